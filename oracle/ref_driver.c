@@ -1,0 +1,318 @@
+/*
+ * TEST INFRASTRUCTURE ONLY — compiled into oracle/_ref/libsdrmodem_ref*.so next to the reference's own
+ * sources (oracle/Makefile). Nothing here is linked into the product library.
+ *
+ * Thin drivers around the reference's public src/dsp API, for the Python tests and bench.py:
+ *   ref_fsk_chain_run      fsk_demod chain composed block by block exactly as
+ *                          reference src/dsp/fsk_demod.c:28-110 does, so that the float soft symbols
+ *                          (clock_mm output) and every intermediate stage can be observed;
+ *   ref_bench_fsk_demod    dsp_worker-style CPU throughput: one pthread per channel slice, each
+ *                          looping fsk_demod_process over its channels' chunks (reference
+ *                          src/dsp_worker.c:44-106 drives the chain the same way);
+ *   ref_bench_gfsk_mod     same for gfsk_mod_process (reference src/tcp_server.c:196).
+ */
+#define _POSIX_C_SOURCE 200809L
+
+#include <complex.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <volk/volk.h>
+
+#include "dsp/clock_recovery_mm.h"
+#include "dsp/dc_blocker.h"
+#include "dsp/fsk_demod.h"
+#include "dsp/gfsk_mod.h"
+#include "dsp/lpf.h"
+#include "dsp/quadrature_demod.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+static double now_seconds(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
+/*
+ * Runs the demod chain over `n` samples in chunks of `chunk`. Any of the stage pointers may be NULL.
+ * Stage buffers must hold n floats (lpf1: 2n floats). Returns number of symbols, or -1.
+ */
+long ref_fsk_chain_run(uint64_t fs, uint32_t baud, int64_t deviation, uint8_t decimation, uint32_t tw, int use_dc,
+                       uint32_t max_len, const float *iq, size_t n, size_t chunk,
+                       float *lpf1_out, float *qd_out, float *lpf2_out, size_t *lpf2_count, float *dc_out,
+                       float *soft_out, int8_t *hard_out, size_t out_cap) {
+    lpf *lpf1 = NULL;
+    lpf *lpf2 = NULL;
+    quadrature_demod *qd = NULL;
+    dc_blocker *dc = NULL;
+    clock_mm *clock = NULL;
+    long result = -1;
+
+    double carson_cutoff = (double) llabs(deviation) + (double) baud / 2;
+    if (lpf_create(1, fs, (uint64_t) carson_cutoff, (uint32_t) (0.1f * carson_cutoff), max_len, sizeof(float complex), &lpf1) != 0) goto done;
+    if (quadrature_demod_create((float) ((double) fs / (2 * M_PI * (double) deviation)), max_len, &qd) != 0) goto done;
+    if (lpf_create(decimation, fs, baud / 2, tw, max_len, sizeof(float), &lpf2) != 0) goto done;
+    float sps = (float) ((double) fs / baud / decimation);
+    if (use_dc) {
+        if (dc_blocker_create((int) ceilf(sps * 32), &dc) != 0) goto done;
+    }
+    if (clock_mm_create(sps, (sps * (float) M_PI) / 100, 0.5f, 0.5f / 8.0f, 0.01f, max_len, &clock) != 0) goto done;
+
+    size_t produced = 0;
+    size_t lpf2_total = 0;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t len = n - off < chunk ? n - off : chunk;
+        float complex *a = NULL;
+        size_t a_len = 0;
+        lpf_process(iq + 2 * off, len, (void **) &a, &a_len, lpf1);
+        if (lpf1_out != NULL && a_len > 0) memcpy(lpf1_out + 2 * off, a, a_len * sizeof(float complex));
+        float *b = NULL;
+        size_t b_len = 0;
+        quadrature_demod_process(a, a_len, &b, &b_len, qd);
+        if (qd_out != NULL && b_len > 0) memcpy(qd_out + off, b, b_len * sizeof(float));
+        float *c = NULL;
+        size_t c_len = 0;
+        lpf_process(b, b_len, (void **) &c, &c_len, lpf2);
+        if (lpf2_out != NULL && c_len > 0) memcpy(lpf2_out + lpf2_total, c, c_len * sizeof(float));
+        float *d = c;
+        size_t d_len = c_len;
+        if (dc != NULL) {
+            dc_blocker_process(c, c_len, &d, &d_len, dc);
+        }
+        if (dc_out != NULL && d_len > 0) memcpy(dc_out + lpf2_total, d, d_len * sizeof(float));
+        lpf2_total += c_len;
+        float *e = NULL;
+        size_t e_len = 0;
+        clock_mm_process(d, d_len, &e, &e_len, clock);
+        if (produced + e_len > out_cap) goto done;
+        if (soft_out != NULL && e_len > 0) memcpy(soft_out + produced, e, e_len * sizeof(float));
+        if (hard_out != NULL && e_len > 0) volk_32f_s32f_convert_8i(hard_out + produced, e, 127.0f, (unsigned int) e_len);
+        produced += e_len;
+    }
+    if (lpf2_count != NULL) *lpf2_count = lpf2_total;
+    result = (long) produced;
+done:
+    lpf_destroy(lpf1);
+    lpf_destroy(lpf2);
+    quadrature_demod_destroy(qd);
+    dc_blocker_destroy(dc);
+    clock_mm_destroy(clock);
+    return result;
+}
+
+/* fsk_demod through the reference's own fsk_demod_* entry points, chunked. */
+long ref_fsk_demod_run(uint64_t fs, uint32_t baud, int64_t deviation, uint8_t decimation, uint32_t tw, int use_dc,
+                       uint32_t max_len, const float *iq, size_t n, size_t chunk, int8_t *out, size_t out_cap) {
+    fsk_demod *demod = NULL;
+    if (fsk_demod_create(fs, baud, deviation, decimation, tw, use_dc != 0, max_len, &demod) != 0) {
+        return -1;
+    }
+    size_t produced = 0;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t len = n - off < chunk ? n - off : chunk;
+        int8_t *o = NULL;
+        size_t o_len = 0;
+        fsk_demod_process((const float complex *) (iq + 2 * off), len, &o, &o_len, demod);
+        if (produced + o_len > out_cap) {
+            fsk_demod_destroy(demod);
+            return -1;
+        }
+        if (o_len > 0) memcpy(out + produced, o, o_len);
+        produced += o_len;
+    }
+    fsk_demod_destroy(demod);
+    return (long) produced;
+}
+
+struct bench_slice {
+    pthread_t thread;
+    int n_channels;
+    uint64_t fs;
+    uint32_t baud;
+    int64_t deviation;
+    uint8_t decimation;
+    uint32_t tw;
+    int use_dc;
+    uint32_t chunk;
+    const float *iq; /* n_channels * n_samples cf32, channel-major; or shared when stride == 0 */
+    size_t stride;   /* floats between channels */
+    size_t n_samples;
+    int passes;
+    uint64_t symbols;
+    int failed;
+};
+
+static void *bench_fsk_thread(void *arg) {
+    struct bench_slice *s = (struct bench_slice *) arg;
+    fsk_demod **demods = calloc((size_t) s->n_channels, sizeof(fsk_demod *));
+    if (demods == NULL) {
+        s->failed = 1;
+        return NULL;
+    }
+    for (int c = 0; c < s->n_channels; c++) {
+        if (fsk_demod_create(s->fs, s->baud, s->deviation, s->decimation, s->tw, s->use_dc != 0, s->chunk, &demods[c]) != 0) {
+            s->failed = 1;
+        }
+    }
+    uint64_t symbols = 0;
+    if (!s->failed) {
+        for (int p = 0; p < s->passes; p++) {
+            for (size_t off = 0; off < s->n_samples; off += s->chunk) {
+                size_t len = s->n_samples - off < s->chunk ? s->n_samples - off : s->chunk;
+                for (int c = 0; c < s->n_channels; c++) {
+                    int8_t *o = NULL;
+                    size_t o_len = 0;
+                    fsk_demod_process((const float complex *) (s->iq + (size_t) c * s->stride + 2 * off), len, &o, &o_len, demods[c]);
+                    symbols += o_len;
+                }
+            }
+        }
+    }
+    for (int c = 0; c < s->n_channels; c++) {
+        fsk_demod_destroy(demods[c]);
+    }
+    free(demods);
+    s->symbols = symbols;
+    return NULL;
+}
+
+/*
+ * n_threads pthreads, channels split evenly; every channel consumes n_samples per pass in `chunk`-sized
+ * calls. Returns wall seconds for all passes (create/destroy excluded by a start barrier is not needed:
+ * creation is ~1 ms per handle and is included in neither numerator nor, materially, the denominator —
+ * callers use passes large enough that it is <1%). Negative on failure.
+ */
+double ref_bench_fsk_demod(uint64_t fs, uint32_t baud, int64_t deviation, uint8_t decimation, uint32_t tw, int use_dc,
+                           uint32_t chunk, const float *iq, size_t stride_floats, size_t n_samples, int n_channels,
+                           int n_threads, int passes, uint64_t *symbols_out) {
+    if (n_threads < 1 || n_channels < n_threads) {
+        return -1.0;
+    }
+    struct bench_slice *slices = calloc((size_t) n_threads, sizeof(struct bench_slice));
+    if (slices == NULL) {
+        return -1.0;
+    }
+    int base = n_channels / n_threads;
+    int extra = n_channels % n_threads;
+    int first = 0;
+    double start = now_seconds();
+    for (int t = 0; t < n_threads; t++) {
+        struct bench_slice *s = &slices[t];
+        s->n_channels = base + (t < extra ? 1 : 0);
+        s->fs = fs;
+        s->baud = baud;
+        s->deviation = deviation;
+        s->decimation = decimation;
+        s->tw = tw;
+        s->use_dc = use_dc;
+        s->chunk = chunk;
+        s->iq = iq + (size_t) first * stride_floats;
+        s->stride = stride_floats;
+        s->n_samples = n_samples;
+        s->passes = passes;
+        first += s->n_channels;
+        pthread_create(&s->thread, NULL, bench_fsk_thread, s);
+    }
+    uint64_t symbols = 0;
+    int failed = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(slices[t].thread, NULL);
+        symbols += slices[t].symbols;
+        failed |= slices[t].failed;
+    }
+    double elapsed = now_seconds() - start;
+    free(slices);
+    if (symbols_out != NULL) *symbols_out = symbols;
+    return failed ? -1.0 : elapsed;
+}
+
+struct mod_slice {
+    pthread_t thread;
+    int n_channels;
+    float sps;
+    float sensitivity;
+    float bt;
+    const uint8_t *bytes;
+    size_t stride;
+    size_t packet_len;
+    int packets;
+    uint64_t samples;
+    int failed;
+};
+
+static void *bench_mod_thread(void *arg) {
+    struct mod_slice *s = (struct mod_slice *) arg;
+    gfsk_mod **mods = calloc((size_t) s->n_channels, sizeof(gfsk_mod *));
+    if (mods == NULL) {
+        s->failed = 1;
+        return NULL;
+    }
+    for (int c = 0; c < s->n_channels; c++) {
+        if (gfsk_mod_create(s->sps, s->sensitivity, s->bt, (uint32_t) s->packet_len, &mods[c]) != 0) {
+            s->failed = 1;
+        }
+    }
+    uint64_t samples = 0;
+    if (!s->failed) {
+        for (int p = 0; p < s->packets; p++) {
+            for (int c = 0; c < s->n_channels; c++) {
+                float complex *o = NULL;
+                size_t o_len = 0;
+                gfsk_mod_process(s->bytes + (size_t) c * s->stride, s->packet_len, &o, &o_len, mods[c]);
+                samples += o_len;
+            }
+        }
+    }
+    for (int c = 0; c < s->n_channels; c++) {
+        gfsk_mod_destroy(mods[c]);
+    }
+    free(mods);
+    s->samples = samples;
+    return NULL;
+}
+
+double ref_bench_gfsk_mod(float sps, float sensitivity, float bt, const uint8_t *bytes, size_t stride, size_t packet_len,
+                          int n_channels, int n_threads, int packets, uint64_t *samples_out) {
+    if (n_threads < 1 || n_channels < n_threads) {
+        return -1.0;
+    }
+    struct mod_slice *slices = calloc((size_t) n_threads, sizeof(struct mod_slice));
+    if (slices == NULL) {
+        return -1.0;
+    }
+    int base = n_channels / n_threads;
+    int extra = n_channels % n_threads;
+    int first = 0;
+    double start = now_seconds();
+    for (int t = 0; t < n_threads; t++) {
+        struct mod_slice *s = &slices[t];
+        s->n_channels = base + (t < extra ? 1 : 0);
+        s->sps = sps;
+        s->sensitivity = sensitivity;
+        s->bt = bt;
+        s->bytes = bytes + (size_t) first * stride;
+        s->stride = stride;
+        s->packet_len = packet_len;
+        s->packets = packets;
+        first += s->n_channels;
+        pthread_create(&s->thread, NULL, bench_mod_thread, s);
+    }
+    uint64_t samples = 0;
+    int failed = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(slices[t].thread, NULL);
+        samples += slices[t].samples;
+        failed |= slices[t].failed;
+    }
+    double elapsed = now_seconds() - start;
+    free(slices);
+    if (samples_out != NULL) *samples_out = samples;
+    return failed ? -1.0 : elapsed;
+}
