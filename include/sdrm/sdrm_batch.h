@@ -1,0 +1,117 @@
+/*
+ * Batch extension of the reference's src/dsp API: N independent channel sessions that share one parameter set run as
+ * one set of kernel launches per call. A reference handle (fsk_demod_create …) is a batch of one.
+ *
+ * What each entry point stands for in the reference:
+ *   sdrm_fsk_demod_batch_create   N x fsk_demod_create            (src/dsp/fsk_demod.c:28-78, called from src/dsp_worker.c:140)
+ *   sdrm_fsk_demod_batch_process  N x fsk_demod_process           (src/dsp/fsk_demod.c:80-110, called from src/dsp_worker.c:75)
+ *   sdrm_fsk_demod_batch_destroy  N x fsk_demod_destroy           (src/dsp/fsk_demod.c:112-135)
+ *
+ * All channels of a batch receive the same number of samples per call (they hang off the same SDR block, reference
+ * src/sdr_worker.c:46). Channel c of a [channels][stride] buffer starts at base + c * stride elements.
+ * Return codes follow the reference: 0, -ENOMEM, -1 for invalid parameters; CUDA failures map to -EIO.
+ * A handle is used by one thread at a time; different handles may be used concurrently.
+ */
+#ifndef SDRM_BATCH_H
+#define SDRM_BATCH_H
+
+#include <complex.h>
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDRM_FLAG_FAST_FMA 1u  /* FIR dot products use fused multiply-add (not bit-identical to the reference) */
+#define SDRM_FLAG_SOFT_OUT 2u  /* also keep the float soft symbols (clock_mm output) */
+
+typedef struct sdrm_fsk_demod_batch_t sdrm_fsk_demod_batch;
+
+typedef struct {
+    uint32_t n_channels;
+    uint64_t sampling_freq;
+    uint32_t baud_rate;
+    int64_t deviation;
+    uint8_t decimation;
+    uint32_t transition_width;
+    bool use_dc_block;
+    uint32_t max_input_buffer_length; /* samples per channel per call, as in the reference */
+    uint32_t max_symbols_per_call;    /* output capacity per channel; 0 = max_input_buffer_length (reference) */
+    uint32_t flags;
+    int device;                       /* CUDA device ordinal, -1 = current */
+} sdrm_fsk_demod_batch_config;
+
+int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_fsk_demod_batch **batch);
+
+/*
+ * Host buffers in, host buffers out; returns when the outputs are in place.
+ * input: cf32 [channels][in_stride], output: int8 [channels][out_stride], output_len: [channels].
+ * soft (optional, needs SDRM_FLAG_SOFT_OUT): float [channels][out_stride].
+ */
+int sdrm_fsk_demod_batch_process(sdrm_fsk_demod_batch *batch, const float complex *input, size_t in_stride,
+                                 size_t input_len, int8_t *output, float *soft, size_t out_stride, uint32_t *output_len);
+
+/*
+ * The same call split in two so that a caller can keep SDRM_MAX_IN_FLIGHT calls in flight: submit copies the input
+ * host->device asynchronously (pinned memory recommended) and enqueues the chain, fetch (below) collects the oldest
+ * call. process == submit + fetch.
+ */
+#define SDRM_MAX_IN_FLIGHT 2
+int sdrm_fsk_demod_batch_submit(sdrm_fsk_demod_batch *batch, const float complex *input, size_t in_stride, size_t input_len);
+
+/*
+ * Device-resident variant: d_input is cf32 [channels][in_stride] in device memory (16-byte aligned, even stride).
+ * Work is enqueued on the batch's streams; results stay on the device until sdrm_fsk_demod_batch_fetch.
+ * Calls may be issued back to back: the serial tail of call k overlaps the filters of call k+1.
+ */
+int sdrm_fsk_demod_batch_process_device(sdrm_fsk_demod_batch *batch, const void *d_input, size_t in_stride,
+                                        size_t input_len);
+
+/* Waits for the oldest un-fetched call and copies its results out (any pointer may be NULL). */
+int sdrm_fsk_demod_batch_fetch(sdrm_fsk_demod_batch *batch, int8_t *output, float *soft, size_t out_stride,
+                               uint32_t *output_len);
+
+/* Forgets the oldest un-fetched call without copying its results (device-resident pipelines). */
+int sdrm_fsk_demod_batch_release(sdrm_fsk_demod_batch *batch);
+
+/* Device pointers of the most recently enqueued call's results: int8 [channels][*out_stride], uint32 [channels]. */
+int sdrm_fsk_demod_batch_device_outputs(sdrm_fsk_demod_batch *batch, const int8_t **d_output, const uint32_t **d_output_len,
+                                        size_t *out_stride);
+
+/* Blocks until everything enqueued so far has finished. */
+int sdrm_fsk_demod_batch_sync(sdrm_fsk_demod_batch *batch);
+
+/* cudaStream_t of the filter stage (for callers that order their own device work against the batch). */
+void *sdrm_fsk_demod_batch_stream(sdrm_fsk_demod_batch *batch);
+/* cudaStream_t of the serial tail (dc blocker, clock recovery). */
+void *sdrm_fsk_demod_batch_tail_stream(sdrm_fsk_demod_batch *batch);
+
+/* Number of kernels launched by this batch since creation (bench.py reports it as gpu_launches). */
+uint64_t sdrm_fsk_demod_batch_launch_count(const sdrm_fsk_demod_batch *batch);
+
+/*
+ * Optional per-stage timing with CUDA events on the launching streams. stage_times synchronises and returns, for the
+ * most recent call, milliseconds of { lpf1+quad-demod kernel, lpf1 history + lpf2 kernel, dc blocker, clock recovery }.
+ */
+int sdrm_fsk_demod_batch_set_profiling(sdrm_fsk_demod_batch *batch, int enabled);
+int sdrm_fsk_demod_batch_stage_times(sdrm_fsk_demod_batch *batch, float ms[4]);
+
+/* Sticky error bits raised on the device (bit 0: clock history overflow, bit 1: symbol capacity reached). */
+int sdrm_fsk_demod_batch_error_flags(sdrm_fsk_demod_batch *batch);
+
+void sdrm_fsk_demod_batch_destroy(sdrm_fsk_demod_batch *batch);
+
+/* Pinned host memory for the host-buffer entry points (pageable memory works too, but copies serialise). */
+void *sdrm_pinned_alloc(size_t bytes);
+void sdrm_pinned_free(void *p);
+
+/* Library/runtime identification: "sdr-modem_b200 <version>; sm_100a; CUDA runtime <n>". */
+const char *sdrm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

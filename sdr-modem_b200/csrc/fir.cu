@@ -1,0 +1,535 @@
+// Streaming decimating FIR over float2 rows for sm_100a, with the quadrature-demod epilogue of the demod chain.
+//
+// What it replaces: reference src/dsp/fir_filter.c:93-144 (fir_filter_process_float / _complex, one
+// volk_32fc_32f_dot_prod_32fc / volk_32f_x2_dot_prod_32f call per output sample) and, in QD_PAIR mode, the
+// conj-multiply + fast_atan2f pass of src/dsp/quadrature_demod.c:57-73 that follows lpf1 in src/dsp/fsk_demod.c:83-87.
+//
+// Arithmetic contract (exact mode): every output is accumulated by ONE thread, sequentially from tap index 0,
+// one accumulator per float2 component, multiply and add rounded separately — the VOLK generic order, so results
+// are bit-identical to the reference. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under
+// --fmad=false (checked with cuobjdump on CUDA 12.9), so the separate roundings are expressed as two FFMA2 with
+// runtime operands the compiler cannot fold:  p = fma(x, h, -0)  == RN(x*h),  acc = fma(acc, 1, p) == RN(acc + p).
+// Fast mode uses a single FFMA2 per tap (same order, fused rounding).
+//
+// Structure: one CTA = one row x TILE outputs; each thread owns R consecutive outputs and slides a register
+// window over the samples (one 16-byte LDS per two taps), taps are broadcast from shared memory as duplicated
+// (h, h) pairs. Samples (tile + halo) and taps are staged by 1-D TMA bulk copies (cp.async.bulk + mbarrier),
+// tap-blocked so that shared memory does not grow with the filter length, double-buffered when there is more
+// than one tap block.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sdrm_cuda.h"
+#include "device_math.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kR = 10;                    // outputs per thread
+constexpr int kTile = kThreads * kR;      // outputs per CTA
+constexpr int kTapBlock = 528;            // multiple of 12 (D=1 window period) and 22 (D=2 window period)
+constexpr int kSlack = 32;                // float2 of read-ahead slack after each staged sample window
+
+struct FirParams {
+    const float2 *in;
+    size_t in_stride;
+    const float2 *hist;
+    int hist_len;
+    const float2 *taps_dup;
+    int n_taps;
+    int decimation;
+    int phase;
+    int n_in;
+    int n_out;
+    int out_mode;
+    void *out;
+    size_t out_stride;
+    int tc_mask;
+    long long tc_head;
+    float qd_gain;
+    const float *atan_table;
+    int tile_stride;    // outputs advanced per tile (kTile, or kTile - 2 with the quad-demod overlap)
+    int first_out;      // index of the first computed output of tile 0 (0, or -2 with the overlap)
+    int stage_samples;  // float2 per stage for samples
+    int n_stages;
+    float2 one;         // (1, 1)    runtime so that the compiler cannot simplify the exact-mode FFMA2 pair
+    float2 negzero;     // (-0, -0)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier. 16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool FAST>
+__device__ __forceinline__ float2 mac2(float2 acc, float2 x, float2 h, float2 one, float2 negzero) {
+    if (FAST) {
+        return __ffma2_rn(x, h, acc);
+    }
+    float2 p = __ffma2_rn(x, h, negzero);
+    return __ffma2_rn(acc, one, p);
+}
+
+template <bool ALIGNED>
+__device__ __forceinline__ float4 ld_pair(const float2 *p) {
+    if (ALIGNED) {
+        return *reinterpret_cast<const float4 *>(p);
+    }
+    float2 a = p[0];
+    float2 b = p[1];
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ float2 lo(const float4 &v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi(const float4 &v) { return make_float2(v.z, v.w); }
+
+// ---- decimation 1: acc[r] += s[j + r] * h[j]; register window of 12 samples, period 12 taps -------------------
+template <bool FAST, bool ALIGNED, bool GUARD>
+__device__ __forceinline__ void fir_d1_body(float2 (&acc)[kR], float4 (&w)[6], const float2 *s, const float2 *hs, int j,
+                                            int n_taps, float2 one, float2 negzero) {
+#pragma unroll
+    for (int u = 0; u < 12; u++) {
+        if (!GUARD || j + u < n_taps) {
+            float2 h = hs[j + u];
+#pragma unroll
+            for (int r = 0; r < kR; r++) {
+                const int e = (u + r) % 12;
+                float2 x = (e & 1) ? hi(w[e >> 1]) : lo(w[e >> 1]);
+                acc[r] = mac2<FAST>(acc[r], x, h, one, negzero);
+            }
+            if (u & 1) {
+                // samples j+u-1 and j+u are no longer needed: refill their slots with j+u+11, j+u+12
+                w[(u - 1) >> 1] = ld_pair<ALIGNED>(s + j + u + 11);
+            }
+        }
+    }
+}
+
+template <bool FAST, bool ALIGNED>
+__device__ __forceinline__ void fir_d1_block(float2 (&acc)[kR], const float2 *s, const float2 *hs, int n_taps, float2 one,
+                                             float2 negzero) {
+    float4 w[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        w[k] = ld_pair<ALIGNED>(s + 2 * k);
+    }
+    int j = 0;
+    for (; j + 12 <= n_taps; j += 12) {
+        fir_d1_body<FAST, ALIGNED, false>(acc, w, s, hs, j, n_taps, one, negzero);
+    }
+    if (j < n_taps) {
+        fir_d1_body<FAST, ALIGNED, true>(acc, w, s, hs, j, n_taps, one, negzero);
+    }
+}
+
+// ---- decimation 2: acc[r] += s[j + 2r] * h[j]; even/odd windows of 11 samples each, period 22 taps ------------
+template <bool FAST, bool ALIGNED, bool GUARD>
+__device__ __forceinline__ void fir_d2_body(float2 (&acc)[kR], float4 (&w)[11], const float2 *s, const float2 *hs, int j,
+                                            int n_taps, float2 one, float2 negzero) {
+#pragma unroll
+    for (int q = 0; q < 11; q++) {
+        if (!GUARD || j + 2 * q < n_taps) {
+            float2 h = hs[j + 2 * q];
+#pragma unroll
+            for (int r = 0; r < kR; r++) {
+                acc[r] = mac2<FAST>(acc[r], lo(w[(q + r) % 11]), h, one, negzero);
+            }
+        }
+        if (!GUARD || j + 2 * q + 1 < n_taps) {
+            float2 h = hs[j + 2 * q + 1];
+#pragma unroll
+            for (int r = 0; r < kR; r++) {
+                acc[r] = mac2<FAST>(acc[r], hi(w[(q + r) % 11]), h, one, negzero);
+            }
+        }
+        if (!GUARD || j + 2 * q + 2 < n_taps) {
+            w[q] = ld_pair<ALIGNED>(s + j + 2 * q + 22);
+        }
+    }
+}
+
+template <bool FAST, bool ALIGNED>
+__device__ __forceinline__ void fir_d2_block(float2 (&acc)[kR], const float2 *s, const float2 *hs, int n_taps, float2 one,
+                                             float2 negzero) {
+    float4 w[11];
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+        w[k] = ld_pair<ALIGNED>(s + 2 * k);
+    }
+    int j = 0;
+    for (; j + 22 <= n_taps; j += 22) {
+        fir_d2_body<FAST, ALIGNED, false>(acc, w, s, hs, j, n_taps, one, negzero);
+    }
+    if (j < n_taps) {
+        fir_d2_body<FAST, ALIGNED, true>(acc, w, s, hs, j, n_taps, one, negzero);
+    }
+}
+
+// Issues the TMA copies for one tap block of one tile: samples v[start, start + count) and taps [j0, j0 + nt).
+// start is even; the window may straddle the history / input boundary and the end of the input.
+__device__ void stage_load(const FirParams &p, int row, long long start, int count, int j0, int nt, float2 *smp, float2 *tps,
+                           uint64_t *bar) {
+    const float2 *hist_row = p.hist + (size_t) row * p.hist_len;
+    const float2 *in_row = p.in + (size_t) row * p.in_stride;
+    long long end = start + count;
+    if (end > p.n_in) {
+        end = p.n_in;
+    }
+    // history part [start, min(end, 0))
+    long long h_end = end < 0 ? end : 0;
+    long long h_cnt = h_end > start ? h_end - start : 0;
+    // input part [max(start, 0), end)
+    long long i_beg = start > 0 ? start : 0;
+    long long i_cnt = end > i_beg ? end - i_beg : 0;
+    long long i_bulk = i_cnt & ~1LL;
+    long long h_bulk = h_cnt & ~1LL;  // h_cnt is even whenever end >= 0 (start and hist boundary are even)
+    // odd leftovers (only at the very end of an odd-length input): plain stores, made visible to the waiters by
+    // the release semantics of the mbarrier arrive that follows
+    if (h_cnt & 1) {
+        smp[h_bulk] = hist_row[p.hist_len + start + h_bulk];
+    }
+    if (i_cnt & 1) {
+        smp[(i_beg - start) + i_bulk] = in_row[i_beg + i_bulk];
+    }
+    uint32_t tap_bytes = (uint32_t) (((nt + 1) & ~1) * sizeof(float2));
+    uint32_t bytes = (uint32_t) ((h_bulk + i_bulk) * sizeof(float2)) + tap_bytes;
+    mbar_expect_tx(bar, bytes);
+    if (h_bulk > 0) {
+        tma_load_1d(smp, hist_row + (p.hist_len + start), (uint32_t) (h_bulk * sizeof(float2)), bar);
+    }
+    if (i_bulk > 0) {
+        tma_load_1d(smp + (i_beg - start), in_row + i_beg, (uint32_t) (i_bulk * sizeof(float2)), bar);
+    }
+    tma_load_1d(tps, p.taps_dup + j0, tap_bytes, bar);
+}
+
+template <int D, bool FAST, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads, D == 1 ? 3 : 2) fir_tile_kernel(const FirParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bars[2];
+    __shared__ float2 last_out[kThreads];
+    __shared__ float atan_s[257];
+
+    const int row = blockIdx.x;
+    const int tile = blockIdx.y;
+    const int tid = threadIdx.x;
+
+    float2 *const smem_f2 = reinterpret_cast<float2 *>(smem_raw);
+    const int stage_f2 = p.stage_samples + kTapBlock;  // per stage: sample window, then the tap block
+
+    // first computed output of this tile and the sample its tap 0 multiplies
+    const long long m0 = (long long) tile * p.tile_stride + p.first_out;
+    const long long v0 = (long long) p.phase + m0 * D - (p.n_taps - 1);
+    const int odd = (int) (v0 & 1);
+    const long long v0_al = v0 - odd;
+    const int window = (kTile - 1) * D + 1;  // samples spanned by the tile's outputs for one tap
+    const int n_blocks = (p.n_taps + kTapBlock - 1) / kTapBlock;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (p.out_mode == SDRM_FIR_OUT_QD_PAIR) {
+        for (int i = tid; i < 257; i += kThreads) {
+            atan_s[i] = p.atan_table[i];
+        }
+    }
+    __syncthreads();
+
+    auto issue = [&](int b, int st) {
+        const int j0 = b * kTapBlock;
+        const int nt = min(kTapBlock, p.n_taps - j0);
+        // taps [j0, j0 + nt) of this tile touch v0 + j0 ... v0 + j0 + window + nt - 2
+        const int count = (odd + window + nt - 1 + 1) & ~1;
+        float2 *smp = smem_f2 + st * stage_f2;
+        stage_load(p, row, v0_al + j0, count, j0, nt, smp, smp + p.stage_samples, &bars[st]);
+    };
+
+    if (tid == 0) {
+        issue(0, 0);
+        if (p.n_stages > 1 && n_blocks > 1) {
+            issue(1, 1);
+        }
+    }
+
+    float2 acc[kR];
+#pragma unroll
+    for (int r = 0; r < kR; r++) {
+        acc[r] = make_float2(0.0f, 0.0f);
+    }
+    const float2 one = p.one;
+    const float2 negzero = p.negzero;
+
+    for (int b = 0; b < n_blocks; b++) {
+        const int st = (p.n_stages > 1) ? (b & 1) : 0;
+        const int nt = min(kTapBlock, p.n_taps - b * kTapBlock);
+        mbar_wait(&bars[st], (uint32_t) ((p.n_stages > 1 ? (b >> 1) : b) & 1));
+        const float2 *smp = smem_f2 + st * stage_f2;
+        const float2 *tps = smp + p.stage_samples;
+        const float2 *s = smp + odd + tid * (kR * D);
+        if (D == 1) {
+            fir_d1_block<FAST, ALIGNED>(acc, s, tps, nt, one, negzero);
+        } else {
+            fir_d2_block<FAST, ALIGNED>(acc, s, tps, nt, one, negzero);
+        }
+        if (b + p.n_stages < n_blocks) {
+            __syncthreads();  // everyone is done reading this stage before TMA overwrites it
+            if (tid == 0) {
+                issue(b + p.n_stages, st);
+            }
+        }
+    }
+
+    const long long m_first = m0 + (long long) tid * kR;
+    if (p.out_mode == SDRM_FIR_OUT_ROWS) {
+        float2 *out = reinterpret_cast<float2 *>(p.out) + (size_t) row * p.out_stride;
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            long long m = m_first + r;
+            if (m < p.n_out) {
+                out[m] = acc[r];
+            }
+        }
+    } else if (p.out_mode == SDRM_FIR_OUT_TC) {
+        float *out = reinterpret_cast<float *>(p.out);
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            long long m = m_first + r;
+            if (m < p.n_out) {
+                size_t ring_row = (size_t) ((p.tc_head + m) & p.tc_mask);
+                *reinterpret_cast<float2 *>(out + ring_row * p.out_stride + 2 * row) = acc[r];
+            }
+        }
+    } else {
+        // quadrature demod: out[o] = gain * atan2(y[o] * conj(y[o-1])); y[o-1] of a thread's first output comes
+        // from its left neighbour; the tile's first two outputs exist only to provide that for the third.
+        last_out[tid] = acc[kR - 1];
+        __syncthreads();
+        float2 prev = tid > 0 ? last_out[tid - 1] : make_float2(0.0f, 0.0f);
+        float *out = reinterpret_cast<float *>(p.out) + (size_t) (row >> 1) * p.out_stride * 2 + (row & 1);
+        const long long emit_from = m0 + 2;
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            long long m = m_first + r;
+            float2 cur = acc[r];
+            if (m >= emit_from && m < p.n_out) {
+                out[2 * m] = sdrm_quad_demod_sample(cur, prev, p.qd_gain, atan_s);
+            }
+            prev = cur;
+        }
+    }
+}
+
+// Any decimation: one thread per output, samples read through L1/L2. Only used where the FIR is a negligible share
+// of the chain (lpf2 behind a large decimation) or for unusual standalone filters.
+template <bool FAST>
+__global__ void fir_generic_kernel(const FirParams p) {
+    const int row = blockIdx.y;
+    const long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= p.n_out) {
+        return;
+    }
+    const float2 *hist_row = p.hist + (size_t) row * p.hist_len + p.hist_len;
+    const float2 *in_row = p.in + (size_t) row * p.in_stride;
+    long long v = (long long) p.phase + m * p.decimation - (p.n_taps - 1);
+    float2 acc = make_float2(0.0f, 0.0f);
+    for (int j = 0; j < p.n_taps; j++, v++) {
+        float2 x = v < 0 ? hist_row[v] : in_row[v];
+        acc = mac2<FAST>(acc, x, p.taps_dup[j], p.one, p.negzero);
+    }
+    if (p.out_mode == SDRM_FIR_OUT_ROWS) {
+        reinterpret_cast<float2 *>(p.out)[(size_t) row * p.out_stride + m] = acc;
+    } else {
+        size_t ring_row = (size_t) ((p.tc_head + m) & p.tc_mask);
+        *reinterpret_cast<float2 *>(reinterpret_cast<float *>(p.out) + ring_row * p.out_stride + 2 * row) = acc;
+    }
+}
+
+__global__ void hist_update_kernel(const float2 *in, size_t in_stride, const float2 *hist, float2 *hist_next, int hist_len,
+                                   int n_in) {
+    const int row = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= hist_len) {
+        return;
+    }
+    long long v = (long long) n_in - hist_len + k;
+    float2 x = v < 0 ? hist[(size_t) row * hist_len + hist_len + v] : in[(size_t) row * in_stride + v];
+    hist_next[(size_t) row * hist_len + k] = x;
+}
+
+__global__ void quad_demod_kernel(const float2 *in, size_t in_stride, float2 *prev, float gain, const float *atan_table,
+                                  float *out, size_t out_stride, int n_in) {
+    __shared__ float atan_s[257];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) {
+        atan_s[i] = atan_table[i];
+    }
+    __syncthreads();
+    const int row = blockIdx.y;
+    const float2 *x = in + (size_t) row * in_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+        float2 before = i > 0 ? x[i - 1] : prev[row];
+        out[(size_t) row * out_stride + i] = sdrm_quad_demod_sample(x[i], before, gain, atan_s);
+    }
+}
+
+__global__ void quad_demod_carry_kernel(const float2 *in, size_t in_stride, float2 *prev, int n_in, int rows) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < rows && n_in > 0) {
+        prev[row] = in[(size_t) row * in_stride + n_in - 1];
+    }
+}
+
+template <int D, bool FAST, bool ALIGNED>
+int launch_tile(const FirParams &p, int rows, int tiles, size_t smem, cudaStream_t stream) {
+    auto kernel = fir_tile_kernel<D, FAST, ALIGNED>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess) {
+        return -(int) err - 1000;
+    }
+    dim3 grid((unsigned) rows, (unsigned) tiles);
+    kernel<<<grid, kThreads, smem, stream>>>(p);
+    err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}
+
+}  // namespace
+
+extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
+    cudaStream_t stream = (cudaStream_t) stream_ptr;
+    if (a->n_out <= 0 || a->rows <= 0) {
+        return 0;
+    }
+    const bool qd = a->out_mode == SDRM_FIR_OUT_QD_PAIR;
+    if (a->n_taps < 1 || a->decimation < 1 || (a->hist_len & 1) || a->hist_len < a->n_taps - 1 + (qd ? 2 : 0) ||
+        (qd && a->decimation != 1)) {
+        return -22;
+    }
+    FirParams p;
+    p.in = (const float2 *) a->in;
+    p.in_stride = a->in_stride;
+    p.hist = (const float2 *) a->hist;
+    p.hist_len = a->hist_len;
+    p.taps_dup = (const float2 *) a->taps_dup;
+    p.n_taps = a->n_taps;
+    p.decimation = a->decimation;
+    p.phase = a->phase;
+    p.n_in = a->n_in;
+    p.n_out = a->n_out;
+    p.out_mode = a->out_mode;
+    p.out = a->out;
+    p.out_stride = a->out_stride;
+    p.tc_mask = a->tc_ring_rows - 1;
+    p.tc_head = a->tc_head;
+    p.qd_gain = a->qd_gain;
+    p.atan_table = a->atan_table;
+    p.one = make_float2(1.0f, 1.0f);
+    p.negzero = make_float2(-0.0f, -0.0f);
+
+    if (a->decimation > 2) {
+        if (qd) {
+            return -22;
+        }
+        p.tile_stride = 0;
+        p.first_out = 0;
+        p.stage_samples = 0;
+        p.n_stages = 0;
+        dim3 grid((unsigned) ((a->n_out + 127) / 128), (unsigned) a->rows);
+        if (a->fast) {
+            fir_generic_kernel<true><<<grid, 128, 0, stream>>>(p);
+        } else {
+            fir_generic_kernel<false><<<grid, 128, 0, stream>>>(p);
+        }
+        cudaError_t err = cudaGetLastError();
+        return err == cudaSuccess ? 0 : -(int) err - 1000;
+    }
+
+    const int D = a->decimation;
+    p.tile_stride = qd ? kTile - 2 : kTile;
+    p.first_out = qd ? -2 : 0;
+    const int n_blocks = (a->n_taps + kTapBlock - 1) / kTapBlock;
+    p.n_stages = n_blocks > 1 ? 2 : 1;
+    p.stage_samples = (((kTile - 1) * D + 1 + kTapBlock + 2 + kSlack) + 1) & ~1;
+    const size_t smem = (size_t) p.n_stages * (p.stage_samples + kTapBlock) * sizeof(float2);
+    const int tiles = (a->n_out + p.tile_stride - 1) / p.tile_stride;
+    // sample windows start on an even float2 (16 bytes) iff phase - (n_taps - 1) + first_out * D is even
+    const long long v0 = (long long) a->phase + (long long) p.first_out * D - (a->n_taps - 1);
+    const bool aligned = ((v0 & 1) == 0) && ((p.tile_stride * D) % 2 == 0) && ((a->in_stride & 1) == 0) &&
+                         (((uintptr_t) a->in & 15) == 0) && (((uintptr_t) a->hist & 15) == 0);
+    if ((((uintptr_t) a->in | (uintptr_t) a->hist | (uintptr_t) a->taps_dup) & 15) != 0 || (a->in_stride & 1)) {
+        return -22;  // TMA bulk copies need 16-byte aligned rows
+    }
+#define SDRM_LAUNCH(DD, FF, AA) return launch_tile<DD, FF, AA>(p, a->rows, tiles, smem, stream)
+    if (D == 1) {
+        if (a->fast) {
+            if (aligned) SDRM_LAUNCH(1, true, true);
+            SDRM_LAUNCH(1, true, false);
+        }
+        if (aligned) SDRM_LAUNCH(1, false, true);
+        SDRM_LAUNCH(1, false, false);
+    }
+    if (a->fast) {
+        if (aligned) SDRM_LAUNCH(2, true, true);
+        SDRM_LAUNCH(2, true, false);
+    }
+    if (aligned) SDRM_LAUNCH(2, false, true);
+    SDRM_LAUNCH(2, false, false);
+#undef SDRM_LAUNCH
+}
+
+extern "C" int sdrm_cu_hist_update(const void *in, size_t in_stride, const void *hist, void *hist_next, int hist_len,
+                                   int n_in, int rows, void *stream_ptr) {
+    if (rows <= 0 || hist_len <= 0) {
+        return 0;
+    }
+    dim3 grid((unsigned) ((hist_len + 255) / 256), (unsigned) rows);
+    hist_update_kernel<<<grid, 256, 0, (cudaStream_t) stream_ptr>>>((const float2 *) in, in_stride, (const float2 *) hist,
+                                                                    (float2 *) hist_next, hist_len, n_in);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}
+
+extern "C" int sdrm_cu_quad_demod(const void *in, size_t in_stride, void *prev, float gain, const float *atan_table,
+                                  float *out, size_t out_stride, int n_in, int rows, void *stream_ptr) {
+    if (rows <= 0 || n_in <= 0) {
+        return 0;
+    }
+    cudaStream_t stream = (cudaStream_t) stream_ptr;
+    int blocks = (n_in + 255) / 256;
+    if (blocks > 1024) {
+        blocks = 1024;
+    }
+    dim3 grid((unsigned) blocks, (unsigned) rows);
+    quad_demod_kernel<<<grid, 256, 0, stream>>>((const float2 *) in, in_stride, (float2 *) prev, gain, atan_table, out,
+                                                out_stride, n_in);
+    quad_demod_carry_kernel<<<(rows + 127) / 128, 128, 0, stream>>>((const float2 *) in, in_stride, (float2 *) prev, n_in, rows);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}

@@ -1,0 +1,124 @@
+/*
+ * Thin C ABI between the C host layer (sdr-modem_b200/host) and the sm_100a kernels (sdr-modem_b200/csrc).
+ * Plain pointers and sizes only. Every launcher enqueues on `stream` (a cudaStream_t passed as void*)
+ * and returns 0 or a negative errno-style code; none of them synchronises.
+ *
+ * Device data layouts used across stages ("rows" never share state):
+ *   CF   complex stream rows       float2 (re, im)              row r at base + r * stride   (float2 units)
+ *   PAIR two real channels per row float2 (ch 2p, ch 2p+1)      row p at base + p * stride   (float2 units)
+ *   TC   time-major real           float  [time][n_ch_padded]   channel fastest
+ */
+#ifndef SDRM_CUDA_H
+#define SDRM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum sdrm_fir_out_mode {
+    SDRM_FIR_OUT_ROWS = 0,    /* float2 out[row * out_stride + m] */
+    SDRM_FIR_OUT_QD_PAIR = 1, /* quadrature demod of the filter output, written into PAIR layout */
+    SDRM_FIR_OUT_TC = 2       /* float2 (two channels) written into the TC ring at row tc_head + m, column 2 * row */
+};
+
+/*
+ * Streaming decimating FIR with real taps over float2 rows (reference src/dsp/fir_filter.c:93-144).
+ * The virtual input of a row is v[i], i in [-hist_len, n_in): `hist` for i < 0, `in` for i >= 0.
+ * Output m (0 <= m < n_out) has newest sample i_m = phase + m * decimation and equals
+ *   sum_{j < n_taps} taps_rev[j] * v[i_m - (n_taps - 1) + j]
+ * accumulated sequentially from j = 0 with one accumulator per component (VOLK generic order).
+ * taps_dup holds the reversed taps duplicated into float2 (h, h).
+ */
+typedef struct {
+    const void *in;
+    size_t in_stride;
+    const void *hist;
+    int hist_len; /* even, >= n_taps - 1 (+2 in QD_PAIR mode) */
+    const void *taps_dup;
+    int n_taps;
+    int decimation;
+    int phase;
+    int n_in;
+    int n_out;
+    int rows;
+    int fast; /* 0: separately rounded multiply and add (bit-exact vs the reference); 1: fused multiply-add */
+    int out_mode;
+    void *out;
+    size_t out_stride;       /* ROWS: float2 per row; QD_PAIR: float2 per pair row; TC: floats per time row */
+    int tc_ring_rows;        /* TC only: power of two */
+    long long tc_head;       /* TC only: absolute row of output 0 */
+    float qd_gain;           /* QD_PAIR only */
+    const float *atan_table; /* QD_PAIR only: 257 floats on the device */
+} sdrm_fir_args;
+
+int sdrm_cu_fir(const sdrm_fir_args *args, void *stream);
+
+/* hist_next[row][k] = v[n_in - hist_len + k]; hist and hist_next must not alias. */
+int sdrm_cu_hist_update(const void *in, size_t in_stride, const void *hist, void *hist_next, int hist_len, int n_in,
+                        int rows, void *stream);
+
+/*
+ * Quadrature demod of CF rows (reference src/dsp/quadrature_demod.c:57-73):
+ * out[row][i] = gain * fast_atan2f(x[i] * conj(x[i-1])), prev[row] carries x[-1] and is updated.
+ */
+int sdrm_cu_quad_demod(const void *in, size_t in_stride, void *prev, float gain, const float *atan_table, float *out,
+                       size_t out_stride, int n_in, int rows, void *stream);
+
+/*
+ * TC ring: the real-valued tail of the chain (lpf2 output -> dc blocker -> clock recovery) lives in a time-major
+ * ring  float ring[ring_rows][tc_stride]  with ring_rows a power of two; absolute row t is stored at
+ * t & (ring_rows - 1). Producers append at `head`, consumers may look back at rows they have not released yet,
+ * so no history is ever copied.
+ *
+ * DC blocker over ring rows [head, head + n_rows), in place (reference src/dsp/dc_blocker.c:105-119).
+ * One lane per channel, serial in time. delay: float [4 * length + (2 * length - 2)][n_ch] delay lines
+ * (zeroed at create); sums: float [4][n_ch]; pos_l / pos_x: cursors into the L-slot and (2L-2)-slot delay lines,
+ * identical for all channels and advanced by the caller (pos + n_rows modulo the line length).
+ */
+int sdrm_cu_dc_blocker(float *ring, size_t tc_stride, int ring_rows, long long head, int n_rows, int n_ch, int length,
+                       float *delay, float *sums, int pos_l, int pos_x, void *stream);
+
+/*
+ * Mueller & Mueller clock recovery + int8 conversion (reference src/dsp/clock_recovery_mm.c:78-139,
+ * src/dsp/fsk_demod.c:106) over ring rows [head - state.history, head + n_rows). Outputs are channel-major.
+ */
+typedef struct {
+    float mu;
+    float omega;
+    float last_sample;
+    int history; /* samples carried from previous calls (reference history_offset) */
+} sdrm_clock_state;
+
+typedef struct {
+    const float *ring;
+    size_t tc_stride;
+    int ring_rows;
+    long long head;
+    int n_rows;
+    int n_ch;
+    int max_history; /* rows guaranteed intact behind head */
+    float omega_mid;
+    float omega_lim;
+    float gain_omega;
+    float gain_mu;
+    const float *mmse_taps; /* device: 129 * 8 floats, row-major, as published (not reversed) */
+    sdrm_clock_state *state;
+    float *soft_out;  /* [n_ch][out_stride] or NULL */
+    int8_t *hard_out; /* [n_ch][out_stride] or NULL */
+    size_t out_stride;
+    uint32_t *out_len; /* [n_ch] */
+    int max_out;       /* reference output_len: the loop stops after this many symbols */
+    int *error_flag;   /* device int; bit 0 set if a channel's carried history exceeded max_history */
+    int fast;          /* 1: the 8-tap interpolator dot product uses fused multiply-add */
+} sdrm_clock_args;
+
+int sdrm_cu_clock_mm(const sdrm_clock_args *args, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,262 @@
+"""ctypes binding of libsdrmodem_b200.so — the same C ABI a C host links against (include/sdrm/*.h).
+
+There is no CPU implementation behind this module: if the shared library (and with it the CUDA kernels) is
+missing, importing fails; if no GPU is present, every create call fails with the CUDA error.
+Used by tests/, bench.py and __graft_entry__.py; it mirrors the reference's block API name for name.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdrmodem_b200.so")
+
+FLAG_FAST_FMA = 1
+FLAG_SOFT_OUT = 2
+MAX_IN_FLIGHT = 2
+
+
+class FskDemodBatchConfig(C.Structure):
+    _fields_ = [("n_channels", C.c_uint32),
+                ("sampling_freq", C.c_uint64),
+                ("baud_rate", C.c_uint32),
+                ("deviation", C.c_int64),
+                ("decimation", C.c_uint8),
+                ("transition_width", C.c_uint32),
+                ("use_dc_block", C.c_bool),
+                ("max_input_buffer_length", C.c_uint32),
+                ("max_symbols_per_call", C.c_uint32),
+                ("flags", C.c_uint32),
+                ("device", C.c_int)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libsdrmodem_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C sdr-modem_b200`); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    lib.sdrm_version.restype = C.c_char_p
+    lib.sdrm_pinned_alloc.restype = vp
+    lib.sdrm_pinned_alloc.argtypes = [sz]
+    lib.sdrm_pinned_free.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_create.argtypes = [C.POINTER(FskDemodBatchConfig), C.POINTER(vp)]
+    lib.sdrm_fsk_demod_batch_process.argtypes = [vp, vp, sz, sz, vp, vp, sz, vp]
+    lib.sdrm_fsk_demod_batch_submit.argtypes = [vp, vp, sz, sz]
+    lib.sdrm_fsk_demod_batch_process_device.argtypes = [vp, vp, sz, sz]
+    lib.sdrm_fsk_demod_batch_fetch.argtypes = [vp, vp, vp, sz, vp]
+    lib.sdrm_fsk_demod_batch_release.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_device_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
+    lib.sdrm_fsk_demod_batch_sync.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_stream.restype = vp
+    lib.sdrm_fsk_demod_batch_stream.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_tail_stream.restype = vp
+    lib.sdrm_fsk_demod_batch_tail_stream.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_launch_count.restype = C.c_uint64
+    lib.sdrm_fsk_demod_batch_launch_count.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_error_flags.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_set_profiling.argtypes = [vp, i32]
+    lib.sdrm_fsk_demod_batch_stage_times.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.sdrm_fsk_demod_batch_destroy.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_destroy.restype = None
+    # reference-named single-channel API
+    lib.fsk_demod_create.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_uint8, C.c_uint32, C.c_bool, C.c_uint32,
+                                     C.POINTER(vp)]
+    lib.fsk_demod_process.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(sz), vp]
+    lib.fsk_demod_process.restype = None
+    lib.fsk_demod_destroy.argtypes = [vp]
+    lib.fsk_demod_destroy.restype = None
+    return lib
+
+
+lib = _load()
+
+
+def version():
+    return lib.sdrm_version().decode()
+
+
+class SdrmError(RuntimeError):
+    pass
+
+
+def _check(code, what):
+    if code != 0:
+        raise SdrmError("%s failed with %d" % (what, code))
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from sdrm_pinned_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib.sdrm_pinned_alloc(self.nbytes)
+        if not self.ptr:
+            raise SdrmError("sdrm_pinned_alloc(%d) failed" % self.nbytes)
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib.sdrm_pinned_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FskDemodBatch:
+    """N x fsk_demod (reference src/dsp/fsk_demod.c) as one batched GPU session."""
+
+    def __init__(self, n_channels, sampling_freq, baud_rate, deviation, decimation, transition_width, use_dc_block,
+                 max_input_buffer_length, max_symbols_per_call=0, fast=False, soft=False, device=-1):
+        cfg = FskDemodBatchConfig(n_channels, sampling_freq, baud_rate, deviation, decimation, transition_width,
+                                  bool(use_dc_block), max_input_buffer_length, max_symbols_per_call,
+                                  (FLAG_FAST_FMA if fast else 0) | (FLAG_SOFT_OUT if soft else 0), device)
+        self.handle = C.c_void_p()
+        self.n_channels = n_channels
+        self.max_len = max_input_buffer_length
+        self.capacity = max_symbols_per_call or max_input_buffer_length
+        self.soft = soft
+        _check(lib.sdrm_fsk_demod_batch_create(C.byref(cfg), C.byref(self.handle)), "sdrm_fsk_demod_batch_create")
+
+    # -- host buffers -------------------------------------------------------------------------------------------
+    def process(self, iq):
+        """iq: complex64 [channels, n]. Returns (hard int8 [channels, cap], lens uint32 [channels], soft or None)."""
+        self.submit(iq)
+        return self.fetch()
+
+    def submit(self, iq):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        assert iq.ndim == 2 and iq.shape[0] == self.n_channels
+        self._keep = iq
+        _check(lib.sdrm_fsk_demod_batch_submit(self.handle, iq.ctypes.data_as(C.c_void_p), iq.shape[1], iq.shape[1]),
+               "sdrm_fsk_demod_batch_submit")
+
+    def submit_ptr(self, host_ptr, in_stride, n):
+        _check(lib.sdrm_fsk_demod_batch_submit(self.handle, host_ptr, in_stride, n), "sdrm_fsk_demod_batch_submit")
+
+    def fetch(self, hard=None, lens=None, soft=None):
+        cap = self.capacity
+        if hard is None:
+            hard = np.zeros((self.n_channels, cap), dtype=np.int8)
+        if lens is None:
+            lens = np.zeros(self.n_channels, dtype=np.uint32)
+        if soft is None and self.soft:
+            soft = np.zeros((self.n_channels, cap), dtype=np.float32)
+        _check(lib.sdrm_fsk_demod_batch_fetch(self.handle, hard.ctypes.data_as(C.c_void_p),
+                                              soft.ctypes.data_as(C.c_void_p) if soft is not None else None,
+                                              hard.shape[1], lens.ctypes.data_as(C.c_void_p)),
+               "sdrm_fsk_demod_batch_fetch")
+        return hard, lens, soft
+
+    def fetch_ptr(self, hard_ptr, out_stride, lens_ptr):
+        _check(lib.sdrm_fsk_demod_batch_fetch(self.handle, hard_ptr, None, out_stride, lens_ptr),
+               "sdrm_fsk_demod_batch_fetch")
+
+    # -- device-resident ----------------------------------------------------------------------------------------
+    def process_device(self, d_ptr, in_stride, n):
+        _check(lib.sdrm_fsk_demod_batch_process_device(self.handle, C.c_void_p(d_ptr), in_stride, n),
+               "sdrm_fsk_demod_batch_process_device")
+
+    def release(self):
+        _check(lib.sdrm_fsk_demod_batch_release(self.handle), "sdrm_fsk_demod_batch_release")
+
+    def device_outputs(self):
+        d_out, d_len, stride = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _check(lib.sdrm_fsk_demod_batch_device_outputs(self.handle, C.byref(d_out), C.byref(d_len), C.byref(stride)),
+               "sdrm_fsk_demod_batch_device_outputs")
+        return d_out.value, d_len.value, stride.value
+
+    def sync(self):
+        _check(lib.sdrm_fsk_demod_batch_sync(self.handle), "sdrm_fsk_demod_batch_sync")
+
+    @property
+    def stream(self):
+        return lib.sdrm_fsk_demod_batch_stream(self.handle)
+
+    @property
+    def tail_stream(self):
+        return lib.sdrm_fsk_demod_batch_tail_stream(self.handle)
+
+    @property
+    def launch_count(self):
+        return lib.sdrm_fsk_demod_batch_launch_count(self.handle)
+
+    def set_profiling(self, enabled=True):
+        _check(lib.sdrm_fsk_demod_batch_set_profiling(self.handle, int(enabled)), "sdrm_fsk_demod_batch_set_profiling")
+
+    def stage_times(self):
+        """ms of (lpf1+quad kernel, lpf1 history + lpf2, dc blocker, clock recovery) for the latest call."""
+        ms = (C.c_float * 4)()
+        _check(lib.sdrm_fsk_demod_batch_stage_times(self.handle, ms), "sdrm_fsk_demod_batch_stage_times")
+        return list(ms)
+
+    def error_flags(self):
+        return lib.sdrm_fsk_demod_batch_error_flags(self.handle)
+
+    def run_stream(self, iq, chunk):
+        """Feeds complex64 [channels, n] in `chunk`-sized calls; returns per-channel (hard, soft) concatenations."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        hard_parts = [[] for _ in range(self.n_channels)]
+        soft_parts = [[] for _ in range(self.n_channels)]
+        for off in range(0, iq.shape[1], chunk):
+            hard, lens, soft = self.process(iq[:, off:off + chunk])
+            for c in range(self.n_channels):
+                hard_parts[c].append(hard[c, :lens[c]].copy())
+                if soft is not None:
+                    soft_parts[c].append(soft[c, :lens[c]].copy())
+        hard_out = [np.concatenate(p) if p else np.zeros(0, np.int8) for p in hard_parts]
+        soft_out = [np.concatenate(p) if p else np.zeros(0, np.float32) for p in soft_parts] if self.soft else None
+        return hard_out, soft_out
+
+    def close(self):
+        if self.handle:
+            lib.sdrm_fsk_demod_batch_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FskDemod:
+    """fsk_demod_create / _process / _destroy, the reference's single-channel entry points."""
+
+    def __init__(self, sampling_freq, baud_rate, deviation, decimation, transition_width, use_dc_block, max_len):
+        self.handle = C.c_void_p()
+        code = lib.fsk_demod_create(sampling_freq, baud_rate, deviation, decimation, transition_width,
+                                    bool(use_dc_block), max_len, C.byref(self.handle))
+        if code != 0:
+            self.handle = C.c_void_p()
+            raise SdrmError("fsk_demod_create failed with %d" % code)
+
+    def process(self, iq):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        out, n = C.c_void_p(), C.c_size_t()
+        lib.fsk_demod_process(iq.ctypes.data_as(C.c_void_p), iq.shape[0], C.byref(out), C.byref(n), self.handle)
+        if not out.value or n.value == 0:
+            return np.zeros(0, dtype=np.int8)
+        return np.frombuffer((C.c_char * n.value).from_address(out.value), dtype=np.int8).copy()
+
+    def run(self, iq, chunk):
+        parts = [self.process(iq[o:o + chunk]) for o in range(0, len(iq), chunk)]
+        return np.concatenate(parts) if parts else np.zeros(0, np.int8)
+
+    def close(self):
+        if self.handle:
+            lib.fsk_demod_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

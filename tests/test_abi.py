@@ -1,0 +1,89 @@
+"""CPU-only: the C-ABI shared library loads here (no GPU) and exports every function include/sdrm/*.h declares;
+without a GPU its entry points fail loudly instead of falling back to a CPU path."""
+import ctypes as C
+import glob
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HEADERS = sorted(glob.glob(os.path.join(ROOT, "include", "sdrm", "*.h")))
+DECL = re.compile(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?[\s\*](\w+)\s*\([^;{]*\)\s*;", re.M | re.S)
+
+
+def declared_functions(path):
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+    names = []
+    for stmt in text.split(";"):
+        m = re.search(r"(\w+)\s*\(", stmt)
+        if m and "typedef" not in stmt and m.group(1) not in ("defined",):
+            names.append(m.group(1))
+    return names
+
+
+def test_headers_exist():
+    names = {os.path.basename(h) for h in HEADERS}
+    for needed in ("fsk_demod.h", "lpf.h", "quadrature_demod.h", "dc_blocker.h", "clock_recovery_mm.h", "sdrm_batch.h"):
+        assert needed in names
+
+
+@pytest.mark.parametrize("header", HEADERS, ids=[os.path.basename(h) for h in HEADERS])
+def test_library_exports_every_declared_symbol(sdrm, header):
+    names = declared_functions(header)
+    assert names, "no declarations parsed from %s" % header
+    for name in names:
+        assert hasattr(sdrm.lib, name), "%s declared in %s but not exported" % (name, os.path.basename(header))
+
+
+def test_headers_compile_as_c99():
+    for header in HEADERS:
+        src = '#include "%s"\nint main(void) { return 0; }\n' % header
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", "-"], input=src.encode(),
+                       check=True)
+
+
+def test_no_cpu_fallback_without_gpu(sdrm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sdrm.SdrmError):
+        sdrm.FskDemodBatch(1, 48000, 4800, 5000, 2, 2000, True, 4096)
+    with pytest.raises(sdrm.SdrmError):
+        sdrm.FskDemod(48000, 4800, 5000, 2, 2000, True, 4096)
+
+
+def test_host_tap_design_matches_oracle(sdrm, port):
+    """create_low_pass_filter runs on the host (it is part of *_create); it must give the oracle's taps bit for bit."""
+    lib = sdrm.lib
+    lib.create_low_pass_filter.argtypes = [C.c_float, C.c_uint64, C.c_uint64, C.c_uint32,
+                                           C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t)]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    for args in ((192000, 9800, 980), (192000, 4800, 2000), (48000, 7400, 740), (2400000, 6200, 620), (8000, 1750, 500)):
+        p, n = C.POINTER(C.c_float)(), C.c_size_t()
+        assert lib.create_low_pass_filter(1.0, *args, C.byref(p), C.byref(n)) == 0
+        taps = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+        libc.free(p)
+        assert np.array_equal(taps.view(np.uint32), port.low_pass_taps(1.0, *args).view(np.uint32))
+    p, n = C.POINTER(C.c_float)(), C.c_size_t()
+    for bad in ((0, 1750, 500), (8000, 5000, 500), (8000, 1750, 0)):  # reference test/test_lpf_taps.c bounds
+        assert lib.create_low_pass_filter(1.0, *bad, C.byref(p), C.byref(n)) == -1
+
+
+def test_host_fast_atan2f_matches_oracle(sdrm, port):
+    lib = sdrm.lib
+    lib.fast_atan2f.restype = C.c_float
+    lib.fast_atan2f.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(0)
+    y = np.concatenate([rng.standard_normal(2000), [0, 0, 1, -1, 0.0039, np.inf]]).astype(np.float32)
+    x = np.concatenate([rng.standard_normal(2000), [0, 1, 0, 0, 1.0, 1]]).astype(np.float32)
+    got = np.array([lib.fast_atan2f(float(a), float(b)) for a, b in zip(y, x)], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), port.fast_atan2f(y, x).view(np.uint32))
