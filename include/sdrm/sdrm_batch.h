@@ -93,7 +93,8 @@ uint64_t sdrm_fsk_demod_batch_launch_count(const sdrm_fsk_demod_batch *batch);
 
 /*
  * Optional per-stage timing with CUDA events on the launching streams. stage_times synchronises and returns, for the
- * most recent call, milliseconds of { lpf1+quad-demod kernel, lpf1 history + lpf2 kernel, dc blocker, clock recovery }.
+ * most recent call, milliseconds of { lpf1+quad-demod kernel, lpf1 history + lpf2 kernel, fused dc blocker + clock
+ * recovery kernel, whole call from the first kernel's start to the tail's end }.
  */
 int sdrm_fsk_demod_batch_set_profiling(sdrm_fsk_demod_batch *batch, int enabled);
 int sdrm_fsk_demod_batch_stage_times(sdrm_fsk_demod_batch *batch, float ms[4]);

@@ -117,6 +117,50 @@ typedef struct {
 
 int sdrm_cu_clock_mm(const sdrm_clock_args *args, void *stream);
 
+/*
+ * Fused serial tail behind fsk_demod: dc blocker (optional) -> clock recovery -> int8 over ring rows
+ * [head, head + n_rows), one lane per channel. The dc blocker's output stays in a per-lane shared-memory ring of
+ * `ring_slots` samples; the samples the reference would carry in its working buffer are saved to / restored from
+ * `carry` (float [ring_slots][delay_stride]) together with `state`.
+ */
+typedef struct {
+    const float *rows; /* TC ring written by the decimating FIR */
+    size_t tc_stride;
+    int ring_rows;
+    long long head;
+    int n_rows;
+    int n_ch;
+    int dc_length;       /* 0: no dc blocker */
+    float *delay;        /* float [4][dc_length][delay_stride] (last L inputs of each moving average), then
+                            float [dx_length][delay_stride] (group delay line, zero-initialised) */
+    int dx_length;       /* >= 2 * dc_length - 2 + 256: the pipeline's first stage writes ahead of its last */
+    float *sums;         /* float [4][delay_stride] */
+    size_t delay_stride; /* channels rounded up (row pitch of delay, sums and carry) */
+    int pos_l;           /* rows processed so far modulo dc_length */
+    int pos_x;           /* rows processed so far modulo dx_length */
+    float omega_mid;
+    float omega_lim;
+    float gain_omega;
+    float gain_mu;
+    const float *mmse_taps;
+    sdrm_clock_state *state;
+    float *carry;
+    int ring_slots; /* power of two >= 128; a lane may carry up to ring_slots - 80 samples between calls */
+    float *soft_out;
+    int8_t *hard_out;
+    size_t out_stride;
+    uint32_t *out_len;
+    int max_out;
+    int *error_flag; /* bit 0: carried samples exceeded the ring; bit 1: symbol capacity reached */
+    int fast;
+} sdrm_tail_args;
+
+int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream);
+
+/* Self test (synchronous): counts sums for which the tail's branch-free division by `length` differs from an IEEE
+ * division, over blocks * 256 * per_thread pseudo-random values. Used by tests only. */
+int sdrm_cu_selftest_div(int length, uint32_t seed, int blocks, int per_thread, unsigned long long *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,7 @@ struct sdrm_fsk_demod_batch_t {
 
     /* dc blocker */
     int dc_len;
+    int dx_len;
     float *d_delay;
     float *d_sums;
     int pos_l;
@@ -78,6 +79,8 @@ struct sdrm_fsk_demod_batch_t {
     float gain_mu;
     float *d_mmse;
     sdrm_clock_state *d_clock;
+    float *d_carry;
+    int ring_slots;
     int *d_error;
 
     /* staging + results, one set per slot */
@@ -197,7 +200,13 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
             code = -1;
             goto fail;
         }
-        code = sdrm_dev_zalloc((void **) &b->d_delay, (size_t) (6 * b->dc_len - 2) * b->n_ch_pad * sizeof(float));
+        if (b->dc_len < 32) {
+            SDRM_LOG_ERROR("dc blocker length %d (fewer than one sample per symbol) is not supported", b->dc_len);
+            code = -1;
+            goto fail;
+        }
+        b->dx_len = 2 * b->dc_len - 2 + 256;
+        code = sdrm_dev_zalloc((void **) &b->d_delay, ((size_t) 4 * b->dc_len + b->dx_len) * b->n_ch_pad * sizeof(float));
         if (code != 0) goto fail;
         code = sdrm_dev_zalloc((void **) &b->d_sums, (size_t) 4 * b->n_ch_pad * sizeof(float));
         if (code != 0) goto fail;
@@ -223,6 +232,18 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
         free(init);
         if (code != 0) goto fail;
     }
+    /* per-lane shared-memory ring of the fused tail: one symbol step + one 32-row block + slack, power of two */
+    b->ring_slots = (int) sdrm_next_pow2((uint64_t) ceilf(sps * 1.01f) + 8 + 2 * 32 + 16 + 8);
+    if (b->ring_slots < 128) {
+        b->ring_slots = 128;
+    }
+    if (b->ring_slots > 1024) {
+        SDRM_LOG_ERROR("samples per symbol %f too large for the fused tail", (double) sps);
+        code = -1;
+        goto fail;
+    }
+    code = sdrm_dev_zalloc((void **) &b->d_carry, (size_t) b->ring_slots * b->n_ch_pad * sizeof(float));
+    if (code != 0) goto fail;
     code = sdrm_dev_zalloc((void **) &b->d_error, sizeof(int));
     if (code != 0) goto fail;
 
@@ -357,34 +378,31 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     SDRM_CUDA_TRY(cudaStreamWaitEvent(b->s_tail, b->ev_fir[slot], 0));
     if (b->profiling) {
         SDRM_CUDA_TRY(cudaEventRecord(b->ev_time[slot][3], b->s_tail));
-    }
-    if (b->dc_len > 0 && n_rows > 0) {
-        code = sdrm_launch_code(sdrm_cu_dc_blocker(b->d_ring, b->tc_stride, (int) b->ring_rows, b->head, n_rows, (int) b->n_ch_pad,
-                                                   b->dc_len, b->d_delay, b->d_sums, b->pos_l, b->pos_x, b->s_tail),
-                                "dc blocker");
-        if (code != 0) return code;
-        b->pos_l = (int) (((long long) b->pos_l + n_rows) % b->dc_len);
-        b->pos_x = (int) (((long long) b->pos_x + n_rows) % (2 * b->dc_len - 2));
-        b->launches += 1;
-    }
-    if (b->profiling) {
         SDRM_CUDA_TRY(cudaEventRecord(b->ev_time[slot][4], b->s_tail));
     }
-    sdrm_clock_args ca;
+    sdrm_tail_args ca;
     memset(&ca, 0, sizeof(ca));
-    ca.ring = b->d_ring;
+    ca.rows = b->d_ring;
     ca.tc_stride = b->tc_stride;
     ca.ring_rows = (int) b->ring_rows;
     ca.head = b->head;
     ca.n_rows = n_rows;
     ca.n_ch = (int) b->n_ch;
-    ca.max_history = b->max_history;
+    ca.dc_length = b->dc_len;
+    ca.delay = b->d_delay;
+    ca.sums = b->d_sums;
+    ca.delay_stride = b->n_ch_pad;
+    ca.dx_length = b->dx_len;
+    ca.pos_l = b->pos_l;
+    ca.pos_x = b->pos_x;
     ca.omega_mid = b->omega_mid;
     ca.omega_lim = b->omega_lim;
     ca.gain_omega = b->gain_omega;
     ca.gain_mu = b->gain_mu;
     ca.mmse_taps = b->d_mmse;
     ca.state = b->d_clock;
+    ca.carry = b->d_carry;
+    ca.ring_slots = b->ring_slots;
     ca.soft_out = b->d_soft[slot];
     ca.hard_out = b->d_hard[slot];
     ca.out_stride = b->out_stride;
@@ -392,7 +410,11 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     ca.max_out = (int) (b->cfg.max_symbols_per_call != 0 ? b->cfg.max_symbols_per_call : b->cfg.max_input_buffer_length);
     ca.error_flag = b->d_error;
     ca.fast = b->fast;
-    code = sdrm_launch_code(sdrm_cu_clock_mm(&ca, b->s_tail), "clock recovery");
+    if (b->dc_len > 0) {
+        b->pos_l = (int) (((long long) b->pos_l + n_rows) % b->dc_len);
+        b->pos_x = (int) (((long long) b->pos_x + n_rows) % b->dx_len);
+    }
+    code = sdrm_launch_code(sdrm_cu_demod_tail(&ca, b->s_tail), "dc blocker + clock recovery");
     if (code != 0) return code;
     b->launches += 1;
     if (b->profiling) {
@@ -550,7 +572,7 @@ int sdrm_fsk_demod_batch_set_profiling(sdrm_fsk_demod_batch *b, int enabled) {
     return 0;
 }
 
-int sdrm_fsk_demod_batch_stage_times(sdrm_fsk_demod_batch *b, float *ms) {
+int sdrm_fsk_demod_batch_stage_times(sdrm_fsk_demod_batch *b, float ms[4]) {
     if (b == NULL || ms == NULL || !b->profiling || b->submitted == 0) {
         return -1;
     }
@@ -559,8 +581,8 @@ int sdrm_fsk_demod_batch_stage_times(sdrm_fsk_demod_batch *b, float *ms) {
     cudaEvent_t *e = b->ev_time[b->last_slot];
     SDRM_CUDA_TRY(cudaEventElapsedTime(&ms[0], e[0], e[1]));
     SDRM_CUDA_TRY(cudaEventElapsedTime(&ms[1], e[1], e[2]));
-    SDRM_CUDA_TRY(cudaEventElapsedTime(&ms[2], e[3], e[4]));
-    SDRM_CUDA_TRY(cudaEventElapsedTime(&ms[3], e[4], e[5]));
+    SDRM_CUDA_TRY(cudaEventElapsedTime(&ms[2], e[4], e[5])); /* fused dc blocker + clock recovery kernel */
+    SDRM_CUDA_TRY(cudaEventElapsedTime(&ms[3], e[0], e[5])); /* whole call, first kernel start to tail end */
     return 0;
 }
 
@@ -597,6 +619,7 @@ void sdrm_fsk_demod_batch_destroy(sdrm_fsk_demod_batch *b) {
     cudaFree(b->d_delay);
     cudaFree(b->d_sums);
     cudaFree(b->d_clock);
+    cudaFree(b->d_carry);
     cudaFree(b->d_error);
     for (int i = 0; i < 2; i++) {
         cudaFree(b->d_hist1[i]);

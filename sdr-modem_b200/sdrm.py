@@ -192,7 +192,7 @@ class FskDemodBatch:
         _check(lib.sdrm_fsk_demod_batch_set_profiling(self.handle, int(enabled)), "sdrm_fsk_demod_batch_set_profiling")
 
     def stage_times(self):
-        """ms of (lpf1+quad kernel, lpf1 history + lpf2, dc blocker, clock recovery) for the latest call."""
+        """ms of (lpf1+quad kernel, lpf1 history + lpf2, fused dc+clock tail kernel, whole call) for the latest call."""
         ms = (C.c_float * 4)()
         _check(lib.sdrm_fsk_demod_batch_stage_times(self.handle, ms), "sdrm_fsk_demod_batch_stage_times")
         return list(ms)
