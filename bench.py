@@ -42,6 +42,7 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--debug-no-tail", action="store_true", help="measurement aid: skip the serial tail (invalid result)")
     return p.parse_args()
 
 
@@ -177,7 +178,7 @@ def main():
     first_channel = rank * n_ch  # channel c of the job is the same signal on any sharding
     cap = int(chunk / shape.decimation / (shape.sampling_freq / shape.baud_rate / shape.decimation) * 1.1) + 64
     batch = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=cap, fast=(args.mode == "fast"),
-                               device=local_rank)
+                               device=local_rank, debug_flags=(0x80000000 if args.debug_no_tail else 0))
 
     # two resident input buffers of 8 * n_ch * chunk bytes each (1 GiB at the defaults) >> 126 MB L2
     n_buf = 2

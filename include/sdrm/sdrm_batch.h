@@ -104,6 +104,44 @@ int sdrm_fsk_demod_batch_error_flags(sdrm_fsk_demod_batch *batch);
 
 void sdrm_fsk_demod_batch_destroy(sdrm_fsk_demod_batch *batch);
 
+/*
+ * N x sig_source (reference src/dsp/sig_source.c): per-channel NCO with carried float phase, optional mix with the input.
+ * freq_hz[c] is the integer frequency the reference passes to sig_source_multiply for channel c on this call
+ * (doppler_process hands it (int64_t) current_freq_difference per call segment, src/dsp/doppler.c:180).
+ */
+typedef struct sdrm_nco_batch_t sdrm_nco_batch;
+
+int sdrm_nco_batch_create(uint32_t n_channels, float amplitude, uint64_t sampling_freq, uint32_t max_output_buffer_length,
+                          int device, sdrm_nco_batch **batch);
+/* host buffers; input == NULL generates the tone (sig_source_process) */
+int sdrm_nco_batch_process(sdrm_nco_batch *batch, const int64_t *freq_hz, const float complex *input, size_t in_stride,
+                           size_t len, float complex *output, size_t out_stride);
+/* device buffers (cf32 rows), asynchronous on the batch's stream */
+int sdrm_nco_batch_process_device(sdrm_nco_batch *batch, const int64_t *freq_hz, const void *d_input, size_t in_stride,
+                                  size_t len, void *d_output, size_t out_stride);
+int sdrm_nco_batch_sync(sdrm_nco_batch *batch);
+void *sdrm_nco_batch_stream(sdrm_nco_batch *batch);
+void sdrm_nco_batch_destroy(sdrm_nco_batch *batch);
+
+/*
+ * N x gfsk_mod (reference src/dsp/gfsk_mod.c:43-148, called from src/tcp_server.c:196,529): bytes in, cf32 out,
+ * 8 * (int) samples_per_symbol output samples per input byte. All channels receive the same number of bytes per call.
+ */
+typedef struct sdrm_gfsk_mod_batch_t sdrm_gfsk_mod_batch;
+
+int sdrm_gfsk_mod_batch_create(uint32_t n_channels, float samples_per_symbol, float sensitivity, float bt,
+                               uint32_t max_input_buffer_length, int device, sdrm_gfsk_mod_batch **batch);
+/* host buffers: input uint8 [channels][in_stride], output cf32 [channels][out_stride] */
+int sdrm_gfsk_mod_batch_process(sdrm_gfsk_mod_batch *batch, const uint8_t *input, size_t in_stride, size_t input_len,
+                                float complex *output, size_t out_stride, size_t *output_len);
+/* device buffers, asynchronous on the batch's stream; d_output rows must be 8-byte aligned */
+int sdrm_gfsk_mod_batch_process_device(sdrm_gfsk_mod_batch *batch, const void *d_input, size_t in_stride, size_t input_len,
+                                       void *d_output, size_t out_stride);
+int sdrm_gfsk_mod_batch_sync(sdrm_gfsk_mod_batch *batch);
+void *sdrm_gfsk_mod_batch_stream(sdrm_gfsk_mod_batch *batch);
+uint64_t sdrm_gfsk_mod_batch_launch_count(const sdrm_gfsk_mod_batch *batch);
+void sdrm_gfsk_mod_batch_destroy(sdrm_gfsk_mod_batch *batch);
+
 /* Pinned host memory for the host-buffer entry points (pageable memory works too, but copies serialise). */
 void *sdrm_pinned_alloc(size_t bytes);
 void sdrm_pinned_free(void *p);

@@ -161,6 +161,59 @@ int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream);
  * division, over blocks * 256 * per_thread pseudo-random values. Used by tests only. */
 int sdrm_cu_selftest_div(int length, uint32_t seed, int blocks, int per_thread, unsigned long long *mismatches);
 
+/*
+ * NCO / mixer (reference src/dsp/sig_source.c:43-75) over CF rows: out = in * amp * exp(j p), p advancing by
+ * step[ch] per sample in float with the reference's +-2pi wrap. in == NULL generates the tone only.
+ * phase_state[ch] carries p between calls; phases is scratch, float [n_ch][phase_stride].
+ */
+typedef struct {
+    const void *in; /* float2 rows or NULL */
+    size_t in_stride;
+    void *out; /* float2 rows */
+    size_t out_stride;
+    const float *step;      /* [n_ch] phase increment per sample, computed in float on the host as the reference does */
+    const float *amplitude; /* [n_ch] */
+    float *phase_state;     /* [n_ch] */
+    float *phases;          /* scratch */
+    size_t phase_stride;
+    int n;
+    int n_ch;
+} sdrm_nco_args;
+
+int sdrm_cu_nco(const sdrm_nco_args *args, void *stream);
+
+/*
+ * Polyphase interpolating FIR (reference src/dsp/interp_fir_filter.c:139-154) over rows of bytes (unpacked to +-1 bits,
+ * MSB first, src/dsp/gfsk_mod.c:109-120) or floats: out[ch][k * I + p] = scale * sum_j w[k + j] * taps_rev[p][j].
+ * history: float [n_ch][branch_taps - 1], the last inputs of the previous calls (zeros at start); updated.
+ */
+typedef struct {
+    const void *in; /* uint8 rows (in_is_bytes) or float rows */
+    size_t in_stride;
+    int in_is_bytes;
+    int n_in; /* inputs per row: bits (8 * bytes) or floats */
+    int n_ch;
+    int interpolation;
+    int branch_taps;
+    const float *taps_rev; /* device, [interpolation][branch_taps], each branch reversed */
+    float *history;
+    int apply_scale;
+    float scale;
+    float *out;
+    size_t out_stride;
+} sdrm_interp_args;
+
+int sdrm_cu_interp_fir(const sdrm_interp_args *args, void *stream);
+
+/*
+ * Frequency modulator (reference src/dsp/frequency_modulator.c:41-60): phase = wrap(phase + increments[m]) in float,
+ * out[m] = cos(phase) + j sin(phase) evaluated in double and rounded to float. increments already hold
+ * sensitivity * input. increments / phases: float [n_ch][stride] (stride % 4 == 0); phases is scratch and may alias
+ * increments. out: float2 rows.
+ */
+int sdrm_cu_freq_mod(const float *increments, float *phases, size_t stride, float *phase_state, void *out,
+                     size_t out_stride, long long n, int n_ch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,84 +125,79 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Fe
     const bool has_dc = PROD == 4;
     const int ring_mask = a.ring_slots - 1;
     const int parity = (b & 1) * kBlockRows * 32;
-    float v[kBlockRows];
     const float *src = warp == 0 ? f.rows + parity + lane : pipe_s + ((size_t) (warp - 1) * 2 + (b & 1)) * kBlockRows * 32 + lane;
+    float *dst = warp < PROD - 1 ? pipe_s + ((size_t) warp * 2 + (b & 1)) * kBlockRows * 32 + lane : nullptr;
+    if (!has_dc) {
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            if (FULL || r < nr) {
+                ring_lane[((history + row0 + r) & ring_mask) * 32] = src[r * 32];
+            }
+        }
+        return;
+    }
+    const float length_f = (float) a.dc_length;
+    // only y[] lives in registers across the block; inputs are re-read from shared memory where they are needed again
+    float y[kBlockRows];
 #pragma unroll
     for (int r = 0; r < kBlockRows; r++) {
         if (FULL || r < nr) {
-            v[r] = src[r * 32];
+            y[r] = __fsub_rn(src[r * 32], f.line[parity + r * 32 + lane]);
         }
     }
-    if (has_dc) {
-        const float length_f = (float) a.dc_length;
-        float y[kBlockRows];
+    if (valid) {
+        // the block's own inputs replace the ones it just consumed (slots are distinct: L >= 32)
+        int slot = (int) (((long long) a.pos_l + row0) % a.dc_length);
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                y[r] = __fsub_rn(v[r], f.line[parity + r * 32 + lane]);
+                line[(size_t) slot * a.delay_stride] = src[r * 32];
             }
+            slot = slot + 1 == a.dc_length ? 0 : slot + 1;
         }
-        if (valid) {
-            // the block's own inputs replace the ones it just consumed (slots are distinct: L >= 32)
-            int slot = (int) (((long long) a.pos_l + row0) % a.dc_length);
+        if (warp == 0) {
+            // group delay line: x[n] goes in now, the last warp reads x[n - (2L - 2)] three steps later; the line is
+            // 2L - 2 + 256 slots long so that the newest writes never reach the oldest reads
+            const int len_x = a.dx_length;
+            int sx = (int) (((long long) a.pos_x + row0) % len_x);
 #pragma unroll
             for (int r = 0; r < kBlockRows; r++) {
                 if (FULL || r < nr) {
-                    line[(size_t) slot * a.delay_stride] = v[r];
+                    dx[(size_t) sx * a.delay_stride] = src[r * 32];
                 }
-                slot = slot + 1 == a.dc_length ? 0 : slot + 1;
-            }
-            if (warp == 0) {
-                // group delay line: x[n] goes in now, the last warp reads x[n - (2L - 2)] three steps later; the line is
-                // 2L - 2 + 256 slots long so that the newest writes never reach the oldest reads
-                const int len_x = a.dx_length;
-                int sx = (int) (((long long) a.pos_x + row0) % len_x);
-#pragma unroll
-                for (int r = 0; r < kBlockRows; r++) {
-                    if (FULL || r < nr) {
-                        dx[(size_t) sx * a.delay_stride] = v[r];
-                    }
-                    sx = sx + 1 == len_x ? 0 : sx + 1;
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < kBlockRows; r++) {
-            if (FULL || r < nr) {
-                sum = __fadd_rn(y[r], sum);
-                y[r] = sum;
-            }
-        }
-        bool redo = false;
-#pragma unroll
-        for (int r = 0; r < kBlockRows; r++) {
-            if (FULL || r < nr) {
-                v[r] = div_by_length(y[r], length_f, rcp, redo);
-            }
-        }
-        if (__any_sync(0xffffffffu, redo)) {
-#pragma unroll
-            for (int r = 0; r < kBlockRows; r++) {
-                if (FULL || r < nr) {
-                    v[r] = __fdiv_rn(y[r], length_f);
-                }
+                sx = sx + 1 == len_x ? 0 : sx + 1;
             }
         }
     }
-    if (warp < PROD - 1) {
-        float *dst = pipe_s + ((size_t) warp * 2 + (b & 1)) * kBlockRows * 32 + lane;
 #pragma unroll
-        for (int r = 0; r < kBlockRows; r++) {
-            if (FULL || r < nr) {
-                dst[r * 32] = v[r];
+    for (int r = 0; r < kBlockRows; r++) {
+        if (FULL || r < nr) {
+            sum = __fadd_rn(y[r], sum);
+            y[r] = sum;
+        }
+    }
+    bool redo = false;
+#pragma unroll
+    for (int r = 0; r < kBlockRows; r++) {
+        if (FULL || r < nr) {
+            const float q = div_by_length(y[r], length_f, rcp, redo);
+            if (warp < PROD - 1) {
+                dst[r * 32] = q;
+            } else {
+                ring_lane[((history + row0 + r) & ring_mask) * 32] = __fsub_rn(f.dx[parity + r * 32 + lane], q);
             }
         }
-    } else {
+    }
+    if (__any_sync(0xffffffffu, redo)) {
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                const float out = has_dc ? __fsub_rn(f.dx[parity + r * 32 + lane], v[r]) : v[r];
-                ring_lane[((history + row0 + r) & ring_mask) * 32] = out;
+                const float q = __fdiv_rn(y[r], length_f);
+                if (warp < PROD - 1) {
+                    dst[r * 32] = q;
+                } else {
+                    ring_lane[((history + row0 + r) & ring_mask) * 32] = __fsub_rn(f.dx[parity + r * 32 + lane], q);
+                }
             }
         }
     }

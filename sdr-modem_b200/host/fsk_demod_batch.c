@@ -414,7 +414,11 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
         b->pos_l = (int) (((long long) b->pos_l + n_rows) % b->dc_len);
         b->pos_x = (int) (((long long) b->pos_x + n_rows) % b->dx_len);
     }
-    code = sdrm_launch_code(sdrm_cu_demod_tail(&ca, b->s_tail), "dc blocker + clock recovery");
+    if (b->cfg.flags & 0x80000000u) {
+        code = 0; /* measurement aid: filters only, no tail (results are meaningless) */
+    } else {
+        code = sdrm_launch_code(sdrm_cu_demod_tail(&ca, b->s_tail), "dc blocker + clock recovery");
+    }
     if (code != 0) return code;
     b->launches += 1;
     if (b->profiling) {

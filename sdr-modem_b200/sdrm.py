@@ -60,6 +60,24 @@ def _load():
     lib.sdrm_fsk_demod_batch_stage_times.argtypes = [vp, C.POINTER(C.c_float)]
     lib.sdrm_fsk_demod_batch_destroy.argtypes = [vp]
     lib.sdrm_fsk_demod_batch_destroy.restype = None
+    lib.sdrm_nco_batch_create.argtypes = [C.c_uint32, C.c_float, C.c_uint64, C.c_uint32, i32, C.POINTER(vp)]
+    lib.sdrm_nco_batch_process.argtypes = [vp, vp, vp, sz, sz, vp, sz]
+    lib.sdrm_nco_batch_process_device.argtypes = [vp, vp, vp, sz, sz, vp, sz]
+    lib.sdrm_nco_batch_sync.argtypes = [vp]
+    lib.sdrm_nco_batch_stream.restype = vp
+    lib.sdrm_nco_batch_stream.argtypes = [vp]
+    lib.sdrm_nco_batch_destroy.argtypes = [vp]
+    lib.sdrm_nco_batch_destroy.restype = None
+    lib.sdrm_gfsk_mod_batch_create.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32, i32, C.POINTER(vp)]
+    lib.sdrm_gfsk_mod_batch_process.argtypes = [vp, vp, sz, sz, vp, sz, C.POINTER(sz)]
+    lib.sdrm_gfsk_mod_batch_process_device.argtypes = [vp, vp, sz, sz, vp, sz]
+    lib.sdrm_gfsk_mod_batch_sync.argtypes = [vp]
+    lib.sdrm_gfsk_mod_batch_stream.restype = vp
+    lib.sdrm_gfsk_mod_batch_stream.argtypes = [vp]
+    lib.sdrm_gfsk_mod_batch_launch_count.restype = C.c_uint64
+    lib.sdrm_gfsk_mod_batch_launch_count.argtypes = [vp]
+    lib.sdrm_gfsk_mod_batch_destroy.argtypes = [vp]
+    lib.sdrm_gfsk_mod_batch_destroy.restype = None
     # reference-named single-channel API
     lib.fsk_demod_create.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_uint8, C.c_uint32, C.c_bool, C.c_uint32,
                                      C.POINTER(vp)]
@@ -114,10 +132,10 @@ class FskDemodBatch:
     """N x fsk_demod (reference src/dsp/fsk_demod.c) as one batched GPU session."""
 
     def __init__(self, n_channels, sampling_freq, baud_rate, deviation, decimation, transition_width, use_dc_block,
-                 max_input_buffer_length, max_symbols_per_call=0, fast=False, soft=False, device=-1):
+                 max_input_buffer_length, max_symbols_per_call=0, fast=False, soft=False, device=-1, debug_flags=0):
         cfg = FskDemodBatchConfig(n_channels, sampling_freq, baud_rate, deviation, decimation, transition_width,
                                   bool(use_dc_block), max_input_buffer_length, max_symbols_per_call,
-                                  (FLAG_FAST_FMA if fast else 0) | (FLAG_SOFT_OUT if soft else 0), device)
+                                  (FLAG_FAST_FMA if fast else 0) | (FLAG_SOFT_OUT if soft else 0) | debug_flags, device)
         self.handle = C.c_void_p()
         self.n_channels = n_channels
         self.max_len = max_input_buffer_length
@@ -253,6 +271,103 @@ class FskDemod:
     def close(self):
         if self.handle:
             lib.fsk_demod_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NcoBatch:
+    """N x sig_source (reference src/dsp/sig_source.c): per-channel NCO with carried float phase."""
+
+    def __init__(self, n_channels, amplitude, sampling_freq, max_len, device=-1):
+        self.handle = C.c_void_p()
+        self.n_channels = n_channels
+        _check(lib.sdrm_nco_batch_create(n_channels, amplitude, sampling_freq, max_len, device, C.byref(self.handle)),
+               "sdrm_nco_batch_create")
+
+    def multiply(self, freq_hz, iq):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        freq = np.ascontiguousarray(freq_hz, dtype=np.int64)
+        out = np.zeros_like(iq)
+        _check(lib.sdrm_nco_batch_process(self.handle, freq.ctypes.data_as(C.c_void_p), iq.ctypes.data_as(C.c_void_p),
+                                          iq.shape[1], iq.shape[1], out.ctypes.data_as(C.c_void_p), iq.shape[1]),
+               "sdrm_nco_batch_process")
+        return out
+
+    def generate(self, freq_hz, n):
+        freq = np.ascontiguousarray(freq_hz, dtype=np.int64)
+        out = np.zeros((self.n_channels, n), dtype=np.complex64)
+        _check(lib.sdrm_nco_batch_process(self.handle, freq.ctypes.data_as(C.c_void_p), None, 0, n,
+                                          out.ctypes.data_as(C.c_void_p), n), "sdrm_nco_batch_process")
+        return out
+
+    def process_device(self, freq_hz, d_in, in_stride, n, d_out, out_stride):
+        freq = np.ascontiguousarray(freq_hz, dtype=np.int64)
+        _check(lib.sdrm_nco_batch_process_device(self.handle, freq.ctypes.data_as(C.c_void_p), C.c_void_p(d_in), in_stride, n,
+                                                 C.c_void_p(d_out), out_stride), "sdrm_nco_batch_process_device")
+
+    def sync(self):
+        _check(lib.sdrm_nco_batch_sync(self.handle), "sdrm_nco_batch_sync")
+
+    @property
+    def stream(self):
+        return lib.sdrm_nco_batch_stream(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib.sdrm_nco_batch_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GfskModBatch:
+    """N x gfsk_mod (reference src/dsp/gfsk_mod.c): bytes in, cf32 out."""
+
+    def __init__(self, n_channels, samples_per_symbol, sensitivity, bt, max_bytes, device=-1):
+        self.handle = C.c_void_p()
+        self.n_channels = n_channels
+        self.interpolation = int(samples_per_symbol)
+        _check(lib.sdrm_gfsk_mod_batch_create(n_channels, samples_per_symbol, sensitivity, bt, max_bytes, device,
+                                              C.byref(self.handle)), "sdrm_gfsk_mod_batch_create")
+
+    def process(self, data):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert data.ndim == 2 and data.shape[0] == self.n_channels
+        n_out = data.shape[1] * 8 * self.interpolation
+        out = np.zeros((self.n_channels, max(n_out, 1)), dtype=np.complex64)
+        produced = C.c_size_t()
+        _check(lib.sdrm_gfsk_mod_batch_process(self.handle, data.ctypes.data_as(C.c_void_p), data.shape[1], data.shape[1],
+                                               out.ctypes.data_as(C.c_void_p), out.shape[1], C.byref(produced)),
+               "sdrm_gfsk_mod_batch_process")
+        return out[:, :produced.value]
+
+    def process_device(self, d_in, in_stride, n_bytes, d_out, out_stride):
+        _check(lib.sdrm_gfsk_mod_batch_process_device(self.handle, C.c_void_p(d_in), in_stride, n_bytes, C.c_void_p(d_out),
+                                                      out_stride), "sdrm_gfsk_mod_batch_process_device")
+
+    def sync(self):
+        _check(lib.sdrm_gfsk_mod_batch_sync(self.handle), "sdrm_gfsk_mod_batch_sync")
+
+    @property
+    def stream(self):
+        return lib.sdrm_gfsk_mod_batch_stream(self.handle)
+
+    @property
+    def launch_count(self):
+        return lib.sdrm_gfsk_mod_batch_launch_count(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib.sdrm_gfsk_mod_batch_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):
