@@ -124,6 +124,35 @@ void *sdrm_nco_batch_stream(sdrm_nco_batch *batch);
 void sdrm_nco_batch_destroy(sdrm_nco_batch *batch);
 
 /*
+ * N x doppler (reference src/dsp/doppler.c:44-190, called from src/dsp_worker.c:68,130 and src/tcp_server.c:202,549):
+ * every channel has its own satellite (TLE), start time and ground station; all share the sample rate, centre frequency
+ * and the number of samples per call. The orbit model runs on the host (twice per channel per second of signal), the
+ * per-sample rotation on the GPU. direction: +1 = rx (doppler_process_rx), -1 = tx (doppler_process_tx).
+ */
+typedef struct sdrm_doppler_batch_t sdrm_doppler_batch;
+
+typedef struct {
+    double latitude;  /* degrees */
+    double longitude; /* degrees */
+    double altitude;  /* km */
+    int64_t constant_offset;
+    int64_t start_time_seconds; /* unix time; 0 = wall clock at the first call, as the reference */
+    char tle[3][80];
+} sdrm_doppler_channel;
+
+int sdrm_doppler_batch_create(uint32_t n_channels, const sdrm_doppler_channel *channels, uint64_t sampling_freq,
+                              uint64_t center_freq, uint32_t max_output_buffer_length, int device, sdrm_doppler_batch **batch);
+/* host buffers, cf32 [channels][stride] */
+int sdrm_doppler_batch_process(sdrm_doppler_batch *batch, int direction, const float complex *input, size_t in_stride,
+                               size_t len, float complex *output, size_t out_stride);
+/* device buffers, asynchronous on the batch's stream */
+int sdrm_doppler_batch_process_device(sdrm_doppler_batch *batch, int direction, const void *d_input, size_t in_stride,
+                                      size_t len, void *d_output, size_t out_stride);
+int sdrm_doppler_batch_sync(sdrm_doppler_batch *batch);
+void *sdrm_doppler_batch_stream(sdrm_doppler_batch *batch);
+void sdrm_doppler_batch_destroy(sdrm_doppler_batch *batch);
+
+/*
  * N x gfsk_mod (reference src/dsp/gfsk_mod.c:43-148, called from src/tcp_server.c:196,529): bytes in, cf32 out,
  * 8 * (int) samples_per_symbol output samples per input byte. All channels receive the same number of bytes per call.
  */

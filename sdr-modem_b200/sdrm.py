@@ -78,6 +78,14 @@ def _load():
     lib.sdrm_gfsk_mod_batch_launch_count.argtypes = [vp]
     lib.sdrm_gfsk_mod_batch_destroy.argtypes = [vp]
     lib.sdrm_gfsk_mod_batch_destroy.restype = None
+    lib.sdrm_doppler_batch_create.argtypes = [C.c_uint32, vp, C.c_uint64, C.c_uint64, C.c_uint32, i32, C.POINTER(vp)]
+    lib.sdrm_doppler_batch_process.argtypes = [vp, i32, vp, sz, sz, vp, sz]
+    lib.sdrm_doppler_batch_process_device.argtypes = [vp, i32, vp, sz, sz, vp, sz]
+    lib.sdrm_doppler_batch_sync.argtypes = [vp]
+    lib.sdrm_doppler_batch_stream.restype = vp
+    lib.sdrm_doppler_batch_stream.argtypes = [vp]
+    lib.sdrm_doppler_batch_destroy.argtypes = [vp]
+    lib.sdrm_doppler_batch_destroy.restype = None
     # reference-named single-channel API
     lib.fsk_demod_create.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_uint8, C.c_uint32, C.c_bool, C.c_uint32,
                                      C.POINTER(vp)]
@@ -271,6 +279,59 @@ class FskDemod:
     def close(self):
         if self.handle:
             lib.fsk_demod_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DopplerChannel(C.Structure):
+    _fields_ = [("latitude", C.c_double), ("longitude", C.c_double), ("altitude", C.c_double),
+                ("constant_offset", C.c_int64), ("start_time_seconds", C.c_int64), ("tle", (C.c_char * 80) * 3)]
+
+
+def doppler_channel(lat, lon, alt, constant_offset, start_time, tle_lines):
+    ch = DopplerChannel(lat, lon, alt, constant_offset, start_time)
+    for i, line in enumerate(tle_lines):
+        raw = line.encode("ascii")[:79]
+        C.memmove(C.addressof(ch.tle[i]), raw + b"\0", len(raw) + 1)
+    return ch
+
+
+class DopplerBatch:
+    """N x doppler (reference src/dsp/doppler.c): host SGP4 schedule + GPU mixer. direction +1 rx, -1 tx."""
+
+    def __init__(self, channels, sampling_freq, center_freq, max_len, device=-1):
+        self.handle = C.c_void_p()
+        self.n_channels = len(channels)
+        arr = (DopplerChannel * len(channels))(*channels)
+        _check(lib.sdrm_doppler_batch_create(len(channels), arr, sampling_freq, center_freq, max_len, device,
+                                             C.byref(self.handle)), "sdrm_doppler_batch_create")
+
+    def process(self, iq, direction=1):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        out = np.zeros_like(iq)
+        _check(lib.sdrm_doppler_batch_process(self.handle, direction, iq.ctypes.data_as(C.c_void_p), iq.shape[1], iq.shape[1],
+                                              out.ctypes.data_as(C.c_void_p), iq.shape[1]), "sdrm_doppler_batch_process")
+        return out
+
+    def process_device(self, d_in, in_stride, n, d_out, out_stride, direction=1):
+        _check(lib.sdrm_doppler_batch_process_device(self.handle, direction, C.c_void_p(d_in), in_stride, n, C.c_void_p(d_out),
+                                                     out_stride), "sdrm_doppler_batch_process_device")
+
+    def sync(self):
+        _check(lib.sdrm_doppler_batch_sync(self.handle), "sdrm_doppler_batch_sync")
+
+    @property
+    def stream(self):
+        return lib.sdrm_doppler_batch_stream(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib.sdrm_doppler_batch_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):
