@@ -108,6 +108,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def k1_traffic(samples_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, scaled to this launch."""
+    path = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    per_sample = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["samples_per_launch"]
+    return per_sample * samples_per_launch
+
+
 def cpu_reference_run(shape, seconds, n_threads=None):
     """The reference's own CPU chain (oracle/_ref, strict build) driven like dsp_worker: one pthread per channel."""
     import torch
@@ -292,7 +303,7 @@ def main():
                        "rounded multiply and add per tap, so its own ceiling is 0.5" % (sm_max, peaks_kind),
         "pipe_frac": achieved / fp32_peak_tflops * (2.0 if args.mode == "exact" else 1.0),
         "kernel_ms": k1, "kernel_share_of_step": k1 / (ms_total / args.steps),
-        "traffic": None,
+        "traffic": k1_traffic(n_ch * chunk),
         "hbm": {"achieved": (in_bytes + in_bytes / 2) / (k1 * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s"},
         "stage_ms": {"lpf1_quad": k1, "lpf2": float(np.mean(k3_ms)), "dc_clock_tail": float(np.mean(tail_ms)),
                      "call_unpipelined": float(np.mean(call_ms))},
