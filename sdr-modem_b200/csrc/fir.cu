@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? 3 : 2) fir_tile_kernel(cons
             long long m = m_first + r;
             if (m < p.n_out) {
                 size_t ring_row = (size_t) ((p.tc_head + m) & p.tc_mask);
-                *reinterpret_cast<float2 *>(out + ring_row * p.out_stride + 2 * row) = acc[r];
+                // GTC layout: [channel group of 32][ring row][32]
+                *reinterpret_cast<float2 *>(out + (((size_t) (row >> 4) * (p.tc_mask + 1) + ring_row) << 5) + ((2 * row) & 31)) = acc[r];
             }
         }
     } else {
@@ -369,7 +370,8 @@ __global__ void fir_generic_kernel(const FirParams p) {
         reinterpret_cast<float2 *>(p.out)[(size_t) row * p.out_stride + m] = acc;
     } else {
         size_t ring_row = (size_t) ((p.tc_head + m) & p.tc_mask);
-        *reinterpret_cast<float2 *>(reinterpret_cast<float *>(p.out) + ring_row * p.out_stride + 2 * row) = acc;
+        *reinterpret_cast<float2 *>(reinterpret_cast<float *>(p.out) + (((size_t) (row >> 4) * (p.tc_mask + 1) + ring_row) << 5) +
+                                    ((2 * row) & 31)) = acc;
     }
 }
 
@@ -414,6 +416,9 @@ int launch_tile(const FirParams &p, int rows, int tiles, size_t smem, cudaStream
     if (err != cudaSuccess) {
         return -(int) err - 1000;
     }
+    // Same (maximum) shared-memory carveout as the tail kernel: an SM whose carveout was sized for one of the two kernels
+    // alone cannot take CTAs of the other until it drains, which serialises the filters of call k+1 against the tail of call k.
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid((unsigned) rows, (unsigned) tiles);
     kernel<<<grid, kThreads, smem, stream>>>(p);
     err = cudaGetLastError();

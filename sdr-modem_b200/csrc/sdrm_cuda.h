@@ -6,7 +6,9 @@
  * Device data layouts used across stages ("rows" never share state):
  *   CF   complex stream rows       float2 (re, im)              row r at base + r * stride   (float2 units)
  *   PAIR two real channels per row float2 (ch 2p, ch 2p+1)      row p at base + p * stride   (float2 units)
- *   TC   time-major real           float  [time][n_ch_padded]   channel fastest
+ *   TC   time-major real           float  [time][n_ch_padded]   channel fastest (per-block handles)
+ *   GTC  grouped time-major real   float  [group][time][32]     groups of 32 channels, so that 32 rows of one group
+ *                                                               are 4 KB of contiguous memory (one TMA bulk copy)
  */
 #ifndef SDRM_CUDA_H
 #define SDRM_CUDA_H
@@ -21,7 +23,7 @@ extern "C" {
 enum sdrm_fir_out_mode {
     SDRM_FIR_OUT_ROWS = 0,    /* float2 out[row * out_stride + m] */
     SDRM_FIR_OUT_QD_PAIR = 1, /* quadrature demod of the filter output, written into PAIR layout */
-    SDRM_FIR_OUT_TC = 2       /* float2 (two channels) written into the TC ring at row tc_head + m, column 2 * row */
+    SDRM_FIR_OUT_TC = 2       /* float2 (two channels) written into the GTC ring at row tc_head + m, channels 2 * row, 2 * row + 1 */
 };
 
 /*
@@ -47,7 +49,7 @@ typedef struct {
     int fast; /* 0: separately rounded multiply and add (bit-exact vs the reference); 1: fused multiply-add */
     int out_mode;
     void *out;
-    size_t out_stride;       /* ROWS: float2 per row; QD_PAIR: float2 per pair row; TC: floats per time row */
+    size_t out_stride;       /* ROWS: float2 per row; QD_PAIR: float2 per pair row; TC: unused */
     int tc_ring_rows;        /* TC only: power of two */
     long long tc_head;       /* TC only: absolute row of output 0 */
     float qd_gain;           /* QD_PAIR only */
@@ -124,15 +126,15 @@ int sdrm_cu_clock_mm(const sdrm_clock_args *args, void *stream);
  * `carry` (float [ring_slots][delay_stride]) together with `state`.
  */
 typedef struct {
-    const float *rows; /* TC ring written by the decimating FIR */
-    size_t tc_stride;
+    const float *rows; /* GTC ring written by the decimating FIR: float [n_groups][ring_rows][32] */
+    int n_groups;      /* channel groups of 32 (delay_stride / 32) */
     int ring_rows;
     long long head;
     int n_rows;
     int n_ch;
     int dc_length;       /* 0: no dc blocker */
-    float *delay;        /* float [4][dc_length][delay_stride] (last L inputs of each moving average), then
-                            float [dx_length][delay_stride] (group delay line, zero-initialised) */
+    float *delay;        /* float [4][n_groups][dc_length][32] (last L inputs of each moving average), then
+                            float [n_groups][dx_length][32] (group delay line); zero-initialised */
     int dx_length;       /* >= 2 * dc_length - 2 + 256: the pipeline's first stage writes ahead of its last */
     float *sums;         /* float [4][delay_stride] */
     size_t delay_stride; /* channels rounded up (row pitch of delay, sums and carry) */

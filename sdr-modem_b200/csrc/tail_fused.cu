@@ -13,10 +13,16 @@
 //               warp 4  clock recovery over everything complete, interpolating straight out of that ring
 //     __syncthreads()
 //
+// Data movement is all TMA bulk copies (cp.async.bulk). Every global array the loop touches is blocked by groups of 32
+// channels ([group][row][32]), so a block of 32 rows of one group is 4 KB of contiguous memory and moves with ONE copy
+// issued by one lane (two when it wraps around a ring): a stage's delayed inputs are fetched into shared memory one
+// block ahead of the arithmetic and complete on an mbarrier; the stage's own inputs go back to its delay line straight
+// from the shared-memory tile they arrived in. No per-row address arithmetic or register staging is left in the loop
+// (per-row LDG/STG, then per-row cp.async, then per-row bulk copies were each measured and were each the bottleneck).
 // Inside a stage and block, only the running sum y[n] = d[n] + y[n-1] is serial (one FADD per row); the 32 subtractions
-// and the 32 divisions by L are independent and unrolled, so a warp has plenty of ILP. The division by the constant L
-// is done branch-free (two Markstein corrections of sum * RN(1/L), checked against IEEE division by
-// sdrm_cu_selftest_div); values outside a safe exponent range redo their block with __fdiv_rn.
+// and the 32 divisions by L are independent and unrolled. The division by the constant L is branch-free (two Markstein
+// corrections of sum * RN(1/L), checked against IEEE division by sdrm_cu_selftest_div); values outside a safe exponent
+// range redo their block with __fdiv_rn.
 // What the reference carries from call to call in its working buffer (clock_recovery_mm.c:127-135) is saved from the
 // shared-memory ring into a small per-channel carry array at the end of the call and reloaded at the start of the next.
 //
@@ -30,8 +36,81 @@
 
 namespace {
 
-constexpr int kBlockRows = 32;  // rows per pipeline step
-constexpr int kGuard = 16;      // slack between what a lane may lag behind and the size of its ring
+constexpr int kBlockRows = 32;             // rows per pipeline step
+constexpr int kTile = kBlockRows * 32;     // floats per [row][lane] tile (4 KB)
+constexpr int kRowBytes = 32 * 4;          // one row of 32 channels
+constexpr int kGuard = 16;                 // slack between what a lane may lag behind and the size of its ring
+constexpr int kTapsFloats = 129 * 8 + 24;  // MMSE bank, padded to a multiple of 128 bytes
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TAIL_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TAIL_WAIT_DONE;\n"
+        "bra TAIL_WAIT_LOOP;\n"
+        "TAIL_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Rows [first, first + n) of a circular array of `len` rows of 32 channels (128 bytes each, contiguous) <-> a tile in
+// shared memory: one TMA bulk copy, or two when the span wraps around the end of the array.
+__device__ __forceinline__ void bulk_load_rows(float *smem_dst, const float *gmem_rows, int first, int n, int len, uint64_t *bar) {
+    const int part = min(n, len - first);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_rows + (size_t) first * 32), "r"(part * kRowBytes), "r"(smem_u32(bar))
+                 : "memory");
+    if (part < n) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(smem_dst + part * 32)),
+                     "l"(gmem_rows), "r"((n - part) * kRowBytes), "r"(smem_u32(bar))
+                     : "memory");
+    }
+}
+
+__device__ __forceinline__ void bulk_store_rows(float *gmem_rows, const float *smem_src, int first, int n, int len) {
+    const int part = min(n, len - first);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_rows + (size_t) first * 32),
+                 "r"(smem_u32(smem_src)), "r"(part * kRowBytes)
+                 : "memory");
+    if (part < n) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_rows), "r"(smem_u32(smem_src + part * 32)),
+                     "r"((n - part) * kRowBytes)
+                     : "memory");
+    }
+}
+
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+// End-of-step wait of the lane that issued a block's bulk stores. The stores have finished READING their shared-memory
+// tile (it is rewritten in the next step); their global writes must be complete before the same slots are fetched
+// again, which is (L - 64) / 32 steps later at the earliest, so up to `slack` younger store groups may stay in flight.
+__device__ __forceinline__ void bulk_wait_step(int slack) {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (slack >= 2) {
+        asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+    } else if (slack == 1) {
+        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+    } else {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+// generic-proxy writes to shared memory become visible to the async proxy (bulk stores issued after the next barrier)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ float slice_pm1(float x) { return x < 0.0f ? -1.0f : 1.0f; }
 
@@ -56,77 +135,72 @@ __device__ __forceinline__ float div_by_length(float sum, float length_f, float 
     return sum == 0.0f ? sum : q2;  // keeps the sign of a zero sum
 }
 
-__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
-                 : "memory");
-}
-
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// What a producer warp needs from global memory for one block, staged into its shared-memory fetch buffers with
-// cp.async so that all of a block's loads are in flight together (ptxas otherwise sinks each register load next to its
-// use and pays one memory round trip per row) and, when the delay lines allow it, one block ahead of the arithmetic:
-//   warp 0            the block's rows of the TC ring,
-//   every MA warp     the stage's own inputs of L rows ago (its delay line),
-//   last MA warp      x[n - (2L - 2)] from the group delay line.
-struct FetchBuffers {
-    float *rows;  // [2][32][32]   (warp 0)
-    float *line;  // [2][32][32]   (this warp's delay line values)
-    float *dx;    // [2][32][32]   (last producer warp)
+// Shared-memory map of one CTA.
+struct Layout {
+    float *taps;     // MMSE bank
+    float *ring;     // [ring_slots][32] clock sample ring
+    float *pipe;     // [PROD - 1][2] tiles handed from stage to stage
+    float *rows;     // [2] tiles: TC ring rows for warp 0
+    float *line;     // [PROD][2] tiles: delayed inputs of each stage
+    float *dx;       // [2] tiles: group delay line values for the last stage
+    uint64_t *bars;  // [PROD][2] mbarriers
 };
 
+// Global arrays are blocked by groups of 32 channels ([group][row][32]), so a block of 32 rows of one group is 4 KB of
+// contiguous memory. These return the group's slice of each array.
+__device__ __forceinline__ const float *group_rows(const sdrm_tail_args &a, int group) {
+    return a.rows + (size_t) group * a.ring_rows * 32;
+}
+__device__ __forceinline__ float *group_line(const sdrm_tail_args &a, int group, int stage) {
+    return a.delay + ((size_t) stage * a.n_groups + group) * a.dc_length * 32;
+}
+__device__ __forceinline__ float *group_dx(const sdrm_tail_args &a, int group) {
+    return a.delay + (size_t) 4 * a.n_groups * a.dc_length * 32 + (size_t) group * a.dx_length * 32;
+}
+
+// One elected lane fetches block b for this warp's stage: its rows of the TC ring (warp 0), the stage's own inputs of L
+// rows ago (its delay line) and, for the last stage, x[n - (2L - 2)] from the group delay line. Completion is counted on
+// the warp's mbarrier of parity b & 1.
 template <int PROD>
-__device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const FetchBuffers &f, int warp, int lane, int ch, int b,
-                                            const float *line, const float *dx) {
+__device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layout &s, int warp, int lane, int group, int b) {
+    if (lane != 0) {
+        return;
+    }
     const bool has_dc = PROD == 4;
     const int row0 = b * kBlockRows;
     const int nr = min(kBlockRows, a.n_rows - row0);
-    const int parity = (b & 1) * kBlockRows * 32;
+    const int parity = b & 1;
+    uint64_t *bar = s.bars + warp * 2 + parity;
+    const int copies = (warp == 0 ? 1 : 0) + (has_dc ? 1 : 0) + (has_dc && warp == PROD - 1 ? 1 : 0);
+    mbar_expect_tx(bar, (uint32_t) (copies * nr * kRowBytes));
     if (warp == 0) {
-        const int tc_mask = a.ring_rows - 1;
-#pragma unroll 8
-        for (int r = 0; r < nr; r++) {
-            cp_async_f32(f.rows + parity + r * 32 + lane, a.rows + (size_t) ((a.head + row0 + r) & tc_mask) * a.tc_stride + ch);
-        }
+        const int first = (int) ((a.head + row0) & (a.ring_rows - 1));
+        bulk_load_rows(s.rows + parity * kTile, group_rows(a, group), first, nr, a.ring_rows, bar);
     }
     if (has_dc) {
-        int slot = (int) (((long long) a.pos_l + row0) % a.dc_length);
-#pragma unroll 8
-        for (int r = 0; r < nr; r++) {
-            cp_async_f32(f.line + parity + r * 32 + lane, line + (size_t) slot * a.delay_stride);
-            slot = slot + 1 == a.dc_length ? 0 : slot + 1;
-        }
+        const int slot = (int) (((long long) a.pos_l + row0) % a.dc_length);
+        bulk_load_rows(s.line + (warp * 2 + parity) * kTile, group_line(a, group, warp), slot, nr, a.dc_length, bar);
         if (warp == PROD - 1) {
-            const int len_x = a.dx_length;
-            int sx = (int) (((long long) a.pos_x + row0 + len_x - (2 * a.dc_length - 2)) % len_x);
-#pragma unroll 8
-            for (int r = 0; r < nr; r++) {
-                cp_async_f32(f.dx + parity + r * 32 + lane, dx + (size_t) sx * a.delay_stride);
-                sx = sx + 1 == len_x ? 0 : sx + 1;
-            }
+            const int sx = (int) (((long long) a.pos_x + row0 + a.dx_length - (2 * a.dc_length - 2)) % a.dx_length);
+            bulk_load_rows(s.dx + parity * kTile, group_dx(a, group), sx, nr, a.dx_length, bar);
         }
     }
-    cp_async_commit();
 }
 
-// One producer warp's arithmetic for one block whose inputs are already staged: moving average
-//   y = in - in[n-L] + y_prev ; out = y / L   (dc_blocker.c:52-64)
-// then hand-over to the next stage's buffer or (last stage) x[n-(2L-2)] - y4 into the clock's sample ring
-// (dc_blocker.c:110-114). FULL blocks carry no per-row guards, so the 32 rows form one basic block.
+// One producer warp's arithmetic for one block whose inputs are staged:
+//   moving average  y = in - in[n-L] + y_prev ; out = y / L                           (dc_blocker.c:52-64)
+//   last stage      x[n-(2L-2)] - y4 appended to the clock's sample ring              (dc_blocker.c:110-114)
+// FULL blocks carry no per-row guards, so the 32 rows form one basic block that ptxas interleaves freely.
 template <int PROD, bool FULL>
-__device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const FetchBuffers &f, int warp, int lane, bool valid,
-                                               int b, int row0, int nr, int history, float &sum, float rcp, float *line,
-                                               float *dx, float *pipe_s, float *ring_lane) {
+__device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Layout &s, int warp, int lane, int group, int b,
+                                               int nr, int history, float &sum, float rcp) {
     const bool has_dc = PROD == 4;
     const int ring_mask = a.ring_slots - 1;
-    const int parity = (b & 1) * kBlockRows * 32;
-    const float *src = warp == 0 ? f.rows + parity + lane : pipe_s + ((size_t) (warp - 1) * 2 + (b & 1)) * kBlockRows * 32 + lane;
-    float *dst = warp < PROD - 1 ? pipe_s + ((size_t) warp * 2 + (b & 1)) * kBlockRows * 32 + lane : nullptr;
+    const int row0 = b * kBlockRows;
+    const int parity = b & 1;
+    const float *in_tile = warp == 0 ? s.rows + parity * kTile : s.pipe + ((warp - 1) * 2 + parity) * kTile;
+    const float *src = in_tile + lane;
+    float *ring_lane = s.ring + lane;
     if (!has_dc) {
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
@@ -136,37 +210,26 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Fe
         }
         return;
     }
+    // the block's own inputs replace the ones it is about to consume: the input tile goes back to the stage's delay line
+    // (slots are distinct: L >= 32) and, for the first stage, to the group delay line, which is 2L - 2 + 256 slots long
+    // so that these writes never reach what the last stage still has to read
+    if (lane == 0) {
+        const int slot = (int) (((long long) a.pos_l + row0) % a.dc_length);
+        bulk_store_rows(group_line(a, group, warp), in_tile, slot, nr, a.dc_length);
+        if (warp == 0) {
+            const int sx = (int) (((long long) a.pos_x + row0) % a.dx_length);
+            bulk_store_rows(group_dx(a, group), in_tile, sx, nr, a.dx_length);
+        }
+        bulk_commit();
+    }
+
     const float length_f = (float) a.dc_length;
-    // only y[] lives in registers across the block; inputs are re-read from shared memory where they are needed again
+    const float *delayed = s.line + (warp * 2 + parity) * kTile + lane;
     float y[kBlockRows];
 #pragma unroll
     for (int r = 0; r < kBlockRows; r++) {
         if (FULL || r < nr) {
-            y[r] = __fsub_rn(src[r * 32], f.line[parity + r * 32 + lane]);
-        }
-    }
-    if (valid) {
-        // the block's own inputs replace the ones it just consumed (slots are distinct: L >= 32)
-        int slot = (int) (((long long) a.pos_l + row0) % a.dc_length);
-#pragma unroll
-        for (int r = 0; r < kBlockRows; r++) {
-            if (FULL || r < nr) {
-                line[(size_t) slot * a.delay_stride] = src[r * 32];
-            }
-            slot = slot + 1 == a.dc_length ? 0 : slot + 1;
-        }
-        if (warp == 0) {
-            // group delay line: x[n] goes in now, the last warp reads x[n - (2L - 2)] three steps later; the line is
-            // 2L - 2 + 256 slots long so that the newest writes never reach the oldest reads
-            const int len_x = a.dx_length;
-            int sx = (int) (((long long) a.pos_x + row0) % len_x);
-#pragma unroll
-            for (int r = 0; r < kBlockRows; r++) {
-                if (FULL || r < nr) {
-                    dx[(size_t) sx * a.delay_stride] = src[r * 32];
-                }
-                sx = sx + 1 == len_x ? 0 : sx + 1;
-            }
+            y[r] = __fsub_rn(src[r * 32], delayed[r * 32]);
         }
     }
 #pragma unroll
@@ -176,6 +239,8 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Fe
             y[r] = sum;
         }
     }
+    float *dst = warp < PROD - 1 ? s.pipe + (warp * 2 + parity) * kTile + lane : nullptr;
+    const float *xd = s.dx + parity * kTile + lane;
     bool redo = false;
 #pragma unroll
     for (int r = 0; r < kBlockRows; r++) {
@@ -184,7 +249,7 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Fe
             if (warp < PROD - 1) {
                 dst[r * 32] = q;
             } else {
-                ring_lane[((history + row0 + r) & ring_mask) * 32] = __fsub_rn(f.dx[parity + r * 32 + lane], q);
+                ring_lane[((history + row0 + r) & ring_mask) * 32] = __fsub_rn(xd[r * 32], q);
             }
         }
     }
@@ -196,31 +261,45 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Fe
                 if (warp < PROD - 1) {
                     dst[r * 32] = q;
                 } else {
-                    ring_lane[((history + row0 + r) & ring_mask) * 32] = __fsub_rn(f.dx[parity + r * 32 + lane], q);
+                    ring_lane[((history + row0 + r) & ring_mask) * 32] = __fsub_rn(xd[r * 32], q);
                 }
             }
         }
     }
+    if (warp < PROD - 1) {
+        fence_async_smem();  // the next stage sends this tile to its delay line with a bulk store
+    }
 }
 
 // PROD producer warps (4 moving averages, or 1 plain copier when the dc blocker is off) + 1 clock warp.
+// All per-channel arrays are padded to a multiple of 32 channels, so every lane owns real memory.
 template <int PROD>
 __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_tail_args a) {
-    extern __shared__ float smem[];
-    float *taps_s = smem;                                 // 129 * 8
-    float *ring_s = smem + 129 * 8 + 8;                   // [ring_slots][32]
-    float *pipe_s = ring_s + (size_t) a.ring_slots * 32;  // [PROD - 1][2][32 rows][32 lanes]
-    float *fetch_s = pipe_s + (size_t) (PROD - 1) * 2 * kBlockRows * 32;  // [PROD + 2][2][32][32]
+    extern __shared__ __align__(128) float smem[];
+    Layout s;
+    s.taps = smem;
+    s.ring = s.taps + kTapsFloats;
+    s.pipe = s.ring + (size_t) a.ring_slots * 32;
+    s.rows = s.pipe + (PROD - 1) * 2 * kTile;
+    s.line = s.rows + 2 * kTile;
+    s.dx = s.line + PROD * 2 * kTile;
+    s.bars = reinterpret_cast<uint64_t *>(s.dx + 2 * kTile);
     const int ring_mask = a.ring_slots - 1;
     for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) {
-        taps_s[i] = a.mmse_taps[i];
+        s.taps[i] = a.mmse_taps[i];
     }
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int ch_raw = blockIdx.x * 32 + lane;
-    const bool valid = ch_raw < a.n_ch;
-    const int ch = valid ? ch_raw : a.n_ch - 1;  // idle lanes shadow the last channel and never write
-    float *ring_lane = ring_s + lane;
+    const int ch0 = blockIdx.x * 32;
+    const int ch = ch0 + lane;
+    const bool valid = ch < a.n_ch;
+    if (threadIdx.x < PROD * 2) {
+        mbar_init(s.bars + threadIdx.x, 1);
+    }
+    if (threadIdx.x == 0) {
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float *ring_lane = s.ring + lane;
 
     const sdrm_clock_state st = a.state[ch];
     int history = st.history;
@@ -235,27 +314,24 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
     }
     const int n_blocks = (a.n_rows + kBlockRows - 1) / kBlockRows;
     const int n_steps = n_blocks + PROD;
-    const int tc_mask = a.ring_rows - 1;
 
     // producer state
     const bool has_dc = PROD == 4;
     float sum = 0.0f;
     float rcp = 0.0f;
-    float *line = nullptr;
-    const int len_x = a.dx_length;
-    float *dx = nullptr;
     if (has_dc && warp < PROD) {
         sum = a.sums[(size_t) warp * a.delay_stride + ch];
         rcp = __frcp_rn((float) a.dc_length);
-        line = a.delay + (size_t) warp * a.dc_length * a.delay_stride + ch;
-        dx = a.delay + (size_t) 4 * a.dc_length * a.delay_stride + ch;
     }
+    // a block's delay-line slots may be fetched one block ahead only if the previous block does not write them
+    const bool lookahead = !has_dc || a.dc_length >= 2 * kBlockRows;
+    const int store_slack = has_dc ? max(0, min(2, (a.dc_length - 2 * kBlockRows) / kBlockRows)) : 0;
 
     // clock state (warp PROD)
     float *soft = a.soft_out != nullptr ? a.soft_out + (size_t) ch * a.out_stride : nullptr;
     int8_t *hard = a.hard_out != nullptr ? a.hard_out + (size_t) ch * a.out_stride : nullptr;
     const int working_len = history + a.n_rows;
-    // clock_recovery_mm.c:94-99: fewer than 8 samples are only buffered (idle lanes never run the loop)
+    // clock_recovery_mm.c:94-99: fewer than 8 samples are only buffered (padding lanes never run the loop)
     const bool run_clock = valid && working_len >= 8;
     int ii = 0;
     int oo = 0;
@@ -265,33 +341,28 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
     float last_sample = st.last_sample;
     bool overflow = false;
 
-    FetchBuffers fb;
-    fb.rows = fetch_s;
-    fb.line = fetch_s + (size_t) (1 + (warp < PROD ? warp : 0)) * 2 * kBlockRows * 32;
-    fb.dx = fetch_s + (size_t) (PROD + 1) * 2 * kBlockRows * 32;
-    // a block's delay-line slots may be fetched one block ahead only if the previous block does not write them
-    const bool lookahead = !has_dc || a.dc_length >= 2 * kBlockRows;
-
     __syncthreads();
     for (int t = 0; t < n_steps; t++) {
         if (warp < PROD) {
             const int b = t - warp;
             if (b >= 0 && b < n_blocks) {
-                const int row0 = b * kBlockRows;
-                const int nr = min(kBlockRows, a.n_rows - row0);
+                const int nr = min(kBlockRows, a.n_rows - b * kBlockRows);
                 if (b == 0 || !lookahead) {
-                    fetch_block<PROD>(a, fb, warp, lane, ch, b, line, dx);
+                    fetch_block<PROD>(a, s, warp, lane, blockIdx.x, b);
                 }
                 if (lookahead && b + 1 < n_blocks) {
-                    fetch_block<PROD>(a, fb, warp, lane, ch, b + 1, line, dx);
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
+                    fetch_block<PROD>(a, s, warp, lane, blockIdx.x, b + 1);
                 }
+                mbar_wait(s.bars + warp * 2 + (b & 1), (uint32_t) ((b >> 1) & 1));
                 if (nr == kBlockRows) {
-                    producer_block<PROD, true>(a, fb, warp, lane, valid, b, row0, nr, history, sum, rcp, line, dx, pipe_s, ring_lane);
+                    producer_block<PROD, true>(a, s, warp, lane, blockIdx.x, b, nr, history, sum, rcp);
                 } else {
-                    producer_block<PROD, false>(a, fb, warp, lane, valid, b, row0, nr, history, sum, rcp, line, dx, pipe_s, ring_lane);
+                    producer_block<PROD, false>(a, s, warp, lane, blockIdx.x, b, nr, history, sum, rcp);
+                }
+                // this block's delay-line stores are done before the step ends: their source tile is recycled two steps
+                // later and the lines are read again at the earliest one block later
+                if (lane == 0) {
+                    bulk_wait_step(store_slack);
                 }
             }
         } else {
@@ -304,7 +375,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                     break;
                 }
                 const int imu = __float2int_rn(__fmul_rn(mu, 128.0f));
-                const float *tp = taps_s + imu * 8;
+                const float *tp = s.taps + imu * 8;
                 // aligned dot product of fir_filter_process_float_single: (ii & 3) earlier samples meet zero taps first
                 const int lead = ii & 3;
                 float acc = 0.0f;
@@ -318,15 +389,15 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                 float out = acc;
                 if (isnan(out)) {  // clock_recovery_mm.c:107-113
                     out = 0.0f;
-                    if (valid && soft != nullptr) soft[oo] = out;
-                    if (valid && hard != nullptr) hard[oo] = 0;
+                    if (soft != nullptr) soft[oo] = out;
+                    if (hard != nullptr) hard[oo] = 0;
                     previous = ii;
                     ii += (int) floorf(omega);
                     oo++;
                     continue;
                 }
-                if (valid && soft != nullptr) soft[oo] = out;
-                if (valid && hard != nullptr) {
+                if (soft != nullptr) soft[oo] = out;
+                if (hard != nullptr) {
                     const float scaled = __fmul_rn(out, 127.0f);
                     hard[oo] = scaled > 127.0f ? (int8_t) 127 : (scaled < -128.0f ? (int8_t) -128 : (int8_t) __float2int_rn(scaled));
                 }
@@ -345,13 +416,13 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
         __syncthreads();
     }
 
-    if (!valid) {
-        return;
-    }
     if (warp < PROD) {
         if (has_dc) {
             a.sums[(size_t) warp * a.delay_stride + ch] = sum;
         }
+        return;
+    }
+    if (!valid) {
         return;
     }
     // clock_recovery_mm.c:127-135: what is left of the working buffer is carried into the next call
@@ -429,19 +500,23 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
     }
     const bool has_dc = args->dc_length != 0;
     if ((args->ring_rows & (args->ring_rows - 1)) != 0 || args->ring_slots < 128 || (args->ring_slots & (args->ring_slots - 1)) != 0 ||
+        (args->delay_stride & 31) != 0 || args->n_groups * 32 != (int) args->delay_stride || (size_t) args->n_ch > args->delay_stride ||
+        (((uintptr_t) args->rows | (uintptr_t) args->delay) & 127) != 0 ||
         (has_dc && (args->dc_length < kBlockRows || args->dx_length < 2 * args->dc_length - 2 + 8 * kBlockRows))) {
         return -22;
     }
     cudaStream_t stream = (cudaStream_t) stream_ptr;
     const int blocks = (args->n_ch + 31) / 32;
     const int prod = has_dc ? 4 : 1;
-    const size_t smem = (129 * 8 + 8 + (size_t) args->ring_slots * 32 + (size_t) (prod - 1) * 2 * kBlockRows * 32 +
-                         (size_t) (prod + 2) * 2 * kBlockRows * 32) * sizeof(float);
+    const size_t floats = (size_t) kTapsFloats + (size_t) args->ring_slots * 32 + (size_t) (prod - 1) * 2 * kTile + 2 * kTile +
+                          (size_t) prod * 2 * kTile + 2 * kTile;
+    const size_t smem = floats * sizeof(float) + (size_t) prod * 2 * sizeof(uint64_t);
     void (*kernel)(const sdrm_tail_args) = has_dc ? demod_tail_kernel<4> : demod_tail_kernel<1>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess) {
         return -(int) err - 1000;
     }
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // see fir.cu
     kernel<<<blocks, (prod + 1) * 32, smem, stream>>>(*args);
     err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;

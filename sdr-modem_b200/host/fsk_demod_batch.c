@@ -121,7 +121,7 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
     b->cfg = *config;
     b->n_ch = config->n_channels;
     b->n_pairs = (b->n_ch + 1) / 2;
-    b->n_ch_pad = 2 * b->n_pairs;
+    b->n_ch_pad = (uint32_t) sdrm_round_up(b->n_ch, 32); /* the tail moves rows of 32 channels with TMA bulk copies */
     b->fast = (config->flags & SDRM_FLAG_FAST_FMA) != 0;
     b->want_soft = (config->flags & SDRM_FLAG_SOFT_OUT) != 0;
     int code = 0;
@@ -383,7 +383,7 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     sdrm_tail_args ca;
     memset(&ca, 0, sizeof(ca));
     ca.rows = b->d_ring;
-    ca.tc_stride = b->tc_stride;
+    ca.n_groups = (int) (b->n_ch_pad / 32);
     ca.ring_rows = (int) b->ring_rows;
     ca.head = b->head;
     ca.n_rows = n_rows;
