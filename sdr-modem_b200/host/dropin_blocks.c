@@ -547,3 +547,44 @@ void clock_mm_destroy(clock_mm *c) {
     free(c->output);
     free(c);
 }
+
+/* ------------------------------------------------------------------------------------------------ mmse interpolator */
+
+#include "../../include/sdrm/mmse_fir_interpolator.h"
+
+struct mmse_fir_interpolator_t {
+    int taps_len;
+    int steps;
+};
+
+int mmse_fir_interpolator_create(mmse_fir_interpolator **interp) {
+    struct mmse_fir_interpolator_t *result = malloc(sizeof(*result));
+    if (result == NULL) {
+        return -ENOMEM;
+    }
+    result->taps_len = 8;
+    result->steps = 128;
+    *interp = result;
+    return 0;
+}
+
+/* One output of the bank selected by rint(mu * 128) (mmse_fir_interpolator.c:188-191). The reference evaluates it with
+ * an aligned dot product that starts at the 16-byte boundary at or below `input` and meets zero taps first
+ * (fir_filter.c:116-121); those leading terms are reproduced because they matter for non-finite neighbours. */
+float mmse_fir_interpolator_process(const float *input, float mu, mmse_fir_interpolator *interp) {
+    const int imu = (int) rint(mu * interp->steps);
+    const float *row = sdrm_host_mmse_table() + (size_t) imu * 8;
+    const size_t lead = ((size_t) input & 15) / sizeof(float);
+    float acc = 0.0f;
+    for (size_t k = lead; k > 0; k--) {
+        acc += *(input - k) * 0.0f;
+    }
+    for (int j = 0; j < 8; j++) {
+        acc += input[j] * row[7 - j];
+    }
+    return acc;
+}
+
+int mmse_fir_interpolator_taps(mmse_fir_interpolator *interp) { return interp->taps_len; }
+
+void mmse_fir_interpolator_destroy(mmse_fir_interpolator *interp) { free(interp); }

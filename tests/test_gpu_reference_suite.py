@@ -1,0 +1,28 @@
+"""GPU: the reference's OWN unit tests (test/test_*.c, compiled unmodified in the build container by
+`make -C oracle dropin-tests` against oracle/shim/check.h) linked against libsdrmodem_b200.so instead of the reference's
+src/dsp. This is the drop-in proof: same sources, same assertions, same fixtures, GPU library underneath.
+The binaries live in oracle/_ref/tests (git-ignored, they travel to the GPU box) and open fixtures by bare name."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+BIN_DIR = os.path.join(ROOT, "oracle", "_ref", "tests")
+TESTS = ["test_lpf", "test_lpf_taps", "test_quadrature_demod", "test_dc_blocker", "test_clock_recovery_mm",
+         "test_mmse_fir_interpolator", "test_sig_source", "test_gaussian_taps", "test_interp_fir_filter",
+         "test_frequency_modulator", "test_gfsk_mod", "test_fsk_demod", "test_doppler", "test_queue"]
+
+
+@pytest.mark.parametrize("name", TESTS)
+def test_reference_test_binary_passes_against_the_gpu_library(name):
+    binary = os.path.join(BIN_DIR, name)
+    if not os.path.exists(binary):
+        pytest.skip("%s was not built (needs /root/reference at build time)" % binary)
+    proc = subprocess.run([binary], cwd=GOLDEN, capture_output=True, text=True, timeout=300)
+    tail = (proc.stdout + proc.stderr)[-2000:]
+    assert proc.returncode == 0, tail
+    assert "0 failed" in proc.stdout, tail
