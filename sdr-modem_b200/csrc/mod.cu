@@ -24,10 +24,21 @@ namespace {
 
 constexpr float kTwoPi = 6.283185307179586476925286766559f;  // (float) (2 * M_PI), frequency_modulator.c:11
 constexpr int kMaxBranchTaps = 64;
+constexpr int kTileRows = 32;              // time steps per shared-memory tile of the walker
+constexpr int kTile = kTileRows * 32;      // floats per [time][lane] tile (4 KB)
 
-// out[ch][k * I + p] = scale * sum_j w[k + j] * rev[p][j],  w = (K - 1 carried inputs, then this call's inputs).
-// BITS: inputs are bits unpacked from bytes; otherwise floats. scale_on: multiply by the sensitivity (separately rounded).
-template <bool BITS>
+// Intermediate layout between the three passes ("GTC", as in the demod tail): float [group][time][32 channels], so that
+// the serial pass, whose lanes are channels, moves 32 time steps of its 32 channels as one contiguous 4 KB tile.
+__device__ __forceinline__ size_t gtc_index(int ch, long long m, size_t rows) {
+    return (((size_t) (ch >> 5) * rows + (size_t) m) << 5) + (ch & 31);
+}
+
+// out[k * I + p] = scale * sum_j w[k + j] * rev[p][j],  w = (K - 1 carried inputs, then this call's inputs).
+// One thread per INPUT k: its K-sample window is gathered once and feeds all I branch filters.
+// BITS: inputs are bits unpacked from bytes; otherwise floats. GTC: lane = channel and the result goes to the grouped
+// layout (batch path); otherwise lane = input index and the result goes to plain rows (interp_fir_filter handle).
+// KU = 8: window held in registers (fully unrolled, guarded by j < K); KU = kMaxBranchTaps: any K, window in local memory.
+template <bool BITS, bool GTC, int KU>
 __global__ void interp_shape_kernel(const sdrm_interp_args a) {
     __shared__ float taps_s[kMaxBranchTaps * 32];  // [p][j], at most 2048 floats (checked by the launcher)
     const int K = a.branch_taps;
@@ -36,30 +47,134 @@ __global__ void interp_shape_kernel(const sdrm_interp_args a) {
         taps_s[i] = a.taps_rev[i];
     }
     __syncthreads();
-    const int ch = blockIdx.y;
-    const long long n_out = (long long) a.n_in * I;
-    const float *hist = a.history + (size_t) ch * (K - 1);
-    const uint8_t *bytes = BITS ? (const uint8_t *) a.in + (size_t) ch * a.in_stride : nullptr;
-    const float *fin = BITS ? nullptr : (const float *) a.in + (size_t) ch * a.in_stride;
-    float *out = a.out + (size_t) ch * a.out_stride;
-    for (long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x; m < n_out; m += (long long) gridDim.x * blockDim.x) {
-        const int k = (int) (m / I);
-        const int p = (int) (m - (long long) k * I);
-        const float *rev = taps_s + p * K;
-        float acc = 0.0f;
-        for (int j = 0; j < K; j++) {
+    int ch;
+    int k_first;
+    int k_step;
+    if (GTC) {
+        // blockIdx.y = channel group; 8 warps stride over the inputs, lanes are the group's channels
+        ch = blockIdx.y * 32 + (threadIdx.x & 31);
+        k_first = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        k_step = gridDim.x * (blockDim.x >> 5);
+    } else {
+        ch = blockIdx.y;
+        k_first = blockIdx.x * blockDim.x + threadIdx.x;
+        k_step = gridDim.x * blockDim.x;
+    }
+    const int chc = ch < a.n_ch ? ch : a.n_ch - 1;  // padding lanes shadow the last channel and write their own column
+    const float *hist = a.history + (size_t) chc * (K - 1);
+    const uint8_t *bytes = BITS ? (const uint8_t *) a.in + (size_t) chc * a.in_stride : nullptr;
+    const float *fin = BITS ? nullptr : (const float *) a.in + (size_t) chc * a.in_stride;
+    for (int k = k_first; k < a.n_in; k += k_step) {
+        float w[KU];
+#pragma unroll(KU == 8 ? 8 : 1)
+        for (int j = 0; j < (KU == 8 ? 8 : K); j++) {
             const int i = k + j - (K - 1);  // index into this call's inputs; negative -> carried history
-            float w;
-            if (i < 0) {
-                w = hist[(K - 1) + i];
+            if (j >= K) {
+                w[j] = 0.0f;
+            } else if (i < 0) {
+                w[j] = hist[(K - 1) + i];
             } else if (BITS) {
-                w = ((bytes[i >> 3] >> (7 - (i & 7))) & 1) ? 1.0f : -1.0f;
+                w[j] = ((bytes[i >> 3] >> (7 - (i & 7))) & 1) ? 1.0f : -1.0f;
             } else {
-                w = fin[i];
+                w[j] = fin[i];
             }
-            acc = __fadd_rn(acc, __fmul_rn(w, rev[j]));
         }
-        out[m] = a.apply_scale ? __fmul_rn(a.scale, acc) : acc;
+        for (int p = 0; p < I; p++) {
+            const float *rev = taps_s + p * K;
+            float acc = 0.0f;
+#pragma unroll(KU == 8 ? 8 : 1)
+            for (int j = 0; j < (KU == 8 ? 8 : K); j++) {
+                if (j < K) {
+                    acc = __fadd_rn(acc, __fmul_rn(w[j], rev[j]));
+                }
+            }
+            const float v = a.apply_scale ? __fmul_rn(a.scale, acc) : acc;
+            const size_t m = (size_t) k * I + p;
+            if (GTC) {
+                a.out[gtc_index(ch, (long long) m, a.out_stride)] = v;
+            } else {
+                a.out[(size_t) ch * a.out_stride + m] = v;
+            }
+        }
+    }
+}
+
+// The batch modulator's first pass (bytes in, GTC out) for K <= 8: a warp takes one 32-bit word of its 32 channels'
+// packets (lane = channel), so the bytes are read once, the +-1 samples never exist as floats (multiplying a tap by
+// +-1 is a sign flip, exact) and every store is a full 128-byte row of the GTC layout.
+// The first word also needs the carried history (floats, zero before the first call) and takes the general route.
+__global__ void __launch_bounds__(256) bits_shape_kernel(const sdrm_interp_args a) {
+    __shared__ float taps_s[8 * 32];  // [p][j]; the launcher checks K <= 8 and I <= 32
+    const int K = a.branch_taps;
+    const int I = a.interpolation;
+    for (int i = threadIdx.x; i < K * I; i += blockDim.x) {
+        taps_s[i] = a.taps_rev[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.y * 32 + lane;
+    const int chc = ch < a.n_ch ? ch : a.n_ch - 1;
+    const float *hist = a.history + (size_t) chc * (K - 1);
+    const uint8_t *bytes = (const uint8_t *) a.in + (size_t) chc * a.in_stride;
+    const int n_bytes = (a.n_in + 7) >> 3;
+    const int n_words = (a.n_in + 31) >> 5;
+    float *out = a.out + (((size_t) blockIdx.y * a.out_stride) << 5) + lane;
+    auto load_word = [&](int wi) {  // 32 stream bits, first bit in the MSB
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int idx = wi * 4 + b;
+            v = (v << 8) | (idx < n_bytes ? (uint32_t) bytes[idx] : 0u);
+        }
+        return v;
+    };
+    for (int wi = blockIdx.x * 8 + (threadIdx.x >> 5); wi < n_words; wi += gridDim.x * 8) {
+        const uint32_t cur = load_word(wi);
+        const int k0 = wi << 5;
+        const int nk = min(32, a.n_in - k0);
+        if (wi == 0) {
+            for (int kk = 0; kk < nk; kk++) {
+                float w[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int i = kk + j - (K - 1);
+                    w[j] = j >= K ? 0.0f : (i < 0 ? hist[(K - 1) + i] : (((cur >> (31 - i)) & 1) ? 1.0f : -1.0f));
+                }
+                for (int p = 0; p < I; p++) {
+                    const float *rev = taps_s + p * K;
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (j < K) {
+                            acc = __fadd_rn(acc, __fmul_rn(w[j], rev[j]));
+                        }
+                    }
+                    out[((size_t) kk * I + p) << 5] = a.apply_scale ? __fmul_rn(a.scale, acc) : acc;
+                }
+            }
+            continue;
+        }
+        const uint64_t comb = ((uint64_t) load_word(wi - 1) << 32) | cur;
+        for (int kk = 0; kk < nk; kk++) {
+            // bit (K - 1 - j) of x is window sample j; a clear bit is the sample -1, i.e. a flipped tap sign
+            const uint32_t flips = ~(uint32_t) (comb >> (31 - kk));
+            uint32_t sgn[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                sgn[j] = (flips << (31 - (K - 1 - j))) & 0x80000000u;  // shift counts of absent taps are unused
+            }
+            for (int p = 0; p < I; p++) {
+                const float *rev = taps_s + p * K;
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (j < K) {
+                        acc = __fadd_rn(acc, __uint_as_float(__float_as_uint(rev[j]) ^ sgn[j]));
+                    }
+                }
+                out[((size_t) (k0 + kk) * I + p) << 5] = a.apply_scale ? __fmul_rn(a.scale, acc) : acc;
+            }
+        }
     }
 }
 
@@ -90,66 +205,147 @@ __global__ void interp_history_kernel(const sdrm_interp_args a) {
 }
 
 __device__ __forceinline__ float wrap_step(float p, float d) {
-    // phase += d; if (phase < -2pi) phase += 2pi; if (phase > 2pi) phase -= 2pi;   both candidates are formed
-    // speculatively so that the serial chain is one add plus one select deep
+    // frequency_modulator.c:50-55: q = p + d; q < -2pi -> q + 2pi; q > 2pi -> q - 2pi.
+    // q - 2pi and q + 2pi are the same magnitude |q| - 2pi carrying q's sign (float add is symmetric in sign), so a
+    // single comparison on |q| selects it: the serial chain is add, add, sign-merge, select (microbench:
+    // tools/microbench/wrap_chain.cu, 20.5 cycles per step against 37 for the two-comparison form).
     const float q = __fadd_rn(p, d);
-    const float up = __fadd_rn(q, kTwoPi);
-    const float down = __fsub_rn(q, kTwoPi);
-    return q < -kTwoPi ? up : (q > kTwoPi ? down : q);
+    const float s = __fsub_rn(fabsf(q), kTwoPi);
+    return fabsf(q) > kTwoPi ? copysignf(s, q) : q;
 }
 
-// lane = channel. pre_add: the phase is advanced before it is used (frequency_modulator) or after (sig_source).
-// increments: [ch][stride] per-sample steps, rows 16-byte aligned. phases: same layout, the phase each sample uses.
-__global__ void phase_walk_kernel(const float *increments, float *phases, size_t stride,
-                                  float *phase_state, int n, int n_ch) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= n_ch) {
-        return;
-    }
-    const float4 *d4 = reinterpret_cast<const float4 *>(increments + (size_t) ch * stride);
-    float4 *p4 = reinterpret_cast<float4 *>(phases + (size_t) ch * stride);
-    float p = phase_state[ch];
-    const int n4 = n >> 2;
-    int i = 0;
-    for (; i + 4 <= n4; i += 4) {
-        float4 d[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            d[u] = d4[i + u];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            float4 o;
-            p = wrap_step(p, d[u].x);
-            o.x = p;
-            p = wrap_step(p, d[u].y);
-            o.y = p;
-            p = wrap_step(p, d[u].z);
-            o.z = p;
-            p = wrap_step(p, d[u].w);
-            o.w = p;
-            p4[i + u] = o;
-        }
-    }
-    const float *dd = increments + (size_t) ch * stride;
-    float *pp = phases + (size_t) ch * stride;
-    for (int m = i * 4; m < n; m++) {
-        p = wrap_step(p, dd[m]);
-        pp[m] = p;
-    }
-    phase_state[ch] = p;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MOD_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MOD_WAIT_DONE;\n"
+        "bra MOD_WAIT_LOOP;\n"
+        "MOD_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
-__global__ void phase_to_iq_kernel(const float *__restrict__ phases, size_t phase_stride, float2 *__restrict__ out,
-                                   size_t out_stride, long long n) {
-    const int ch = blockIdx.y;
-    const float *ph = phases + (size_t) ch * phase_stride;
-    float2 *y = out + (size_t) ch * out_stride;
-    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
-        double s;
-        double c;
-        sincos((double) ph[i], &s, &c);
-        y[i] = make_float2((float) c, (float) s);
+// The serial pass: phase = wrap(phase + increment[m]), one warp per group of 32 channels, lane = channel.
+// The increments stream in as 4 KB tiles (32 time steps x 32 channels, contiguous in the GTC layout) through a ring of
+// kStages TMA bulk copies, the phases go back the same way in place, so that the recurrence itself — one dependent add
+// and select per sample — is all the warp waits for.
+constexpr int kWalkRows = 128;            // time steps per walker tile: 16 KB per bulk copy amortises the per-tile
+constexpr int kWalkTile = kWalkRows * 32;  // barrier / fence / issue overhead (~450 cycles) over 128 serial steps
+constexpr int kStages = 6;                // tiles in the ring (96 KB of dynamic shared memory)
+constexpr int kPrefetch = 3;  // loads run this many tiles ahead; a stage is reloaded kStages - kPrefetch tiles after its store
+constexpr int kWalkSmem = kStages * kWalkTile * 4 + kStages * 8;
+
+__global__ void __launch_bounds__(32) phase_walk_kernel(float *work, size_t rows, float *phase_state, long long n, int n_ch) {
+    extern __shared__ __align__(128) unsigned char walk_smem[];
+    float(*tiles)[kWalkTile] = reinterpret_cast<float(*)[kWalkTile]>(walk_smem);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(walk_smem + kStages * kWalkTile * 4);
+    const int lane = threadIdx.x;
+    const int group = blockIdx.x;
+    const int ch = group * 32 + lane;
+    float *base = work + (size_t) group * rows * 32;
+    const long long n_tiles = (n + kWalkRows - 1) / kWalkRows;
+    if (lane == 0) {
+        for (int s = 0; s < kStages; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto fetch = [&](long long t) {
+        const int s = (int) (t % kStages);
+        const int nr = (int) min((long long) kWalkRows, n - t * kWalkRows);
+        const uint32_t bytes = (uint32_t) nr * 128u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(tiles[s])),
+                     "l"(base + (size_t) t * kWalkTile), "r"(bytes), "r"(smem_u32(&bars[s]))
+                     : "memory");
+    };
+    if (lane == 0) {
+        for (long long t = 0; t < kPrefetch && t < n_tiles; t++) {
+            fetch(t);
+        }
+    }
+    float p = ch < n_ch ? phase_state[ch] : 0.0f;
+    for (long long t = 0; t < n_tiles; t++) {
+        const int s = (int) (t % kStages);
+        if (lane == 0 && t + kPrefetch < n_tiles) {
+            // the stage being refilled was stored kStages - kPrefetch tiles ago: all but the newest
+            // kStages - kPrefetch - 1 bulk stores must have finished reading shared memory
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStages - kPrefetch - 1) : "memory");
+            fetch(t + kPrefetch);
+        }
+        __syncwarp();
+        mbar_wait(&bars[s], (uint32_t) ((t / kStages) & 1));
+        float *tile = tiles[s] + lane;
+        const int nr = (int) min((long long) kWalkRows, n - t * kWalkRows);
+        if (nr == kWalkRows) {
+            for (int r0 = 0; r0 < kWalkRows; r0 += 32) {
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    p = wrap_step(p, tile[(r0 + r) * 32]);
+                    tile[(r0 + r) * 32] = p;
+                }
+            }
+        } else {
+            for (int r = 0; r < nr; r++) {
+                p = wrap_step(p, tile[r * 32]);
+                tile[r * 32] = p;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + (size_t) t * kWalkTile),
+                         "r"(smem_u32(tiles[s])), "r"((uint32_t) nr * 128u)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (ch < n_ch) {
+        phase_state[ch] = p;
+    }
+}
+
+// out[ch][m] = (float) cos(p) + j (float) sin(p), p from the GTC layout. A block takes a [32 time][32 channel] tile
+// (coalesced: 32 channels are contiguous), turns it through shared memory so that lanes become time, and each warp
+// writes 256-byte runs of one channel's cf32 row.
+__global__ void __launch_bounds__(256) phase_to_iq_kernel(const float *__restrict__ phases, size_t rows, float2 *__restrict__ out,
+                                                          size_t out_stride, long long n, int n_ch) {
+    __shared__ float tile[kTileRows][33];
+    const int group = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const float *base = phases + (size_t) group * rows * 32;
+    const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long m0 = t * kTileRows;
+#pragma unroll
+        for (int r = warp; r < kTileRows; r += 8) {
+            if (m0 + r < n) {
+                tile[r][lane] = base[(size_t) (m0 + r) * 32 + lane];
+            }
+        }
+        __syncthreads();
+        const long long m = m0 + lane;
+#pragma unroll
+        for (int c = warp; c < 32; c += 8) {
+            const int ch = group * 32 + c;
+            if (m < n && ch < n_ch) {
+                double s;
+                double co;
+                sincos((double) tile[lane][c], &s, &co);
+                out[(size_t) ch * out_stride + m] = make_float2((float) co, (float) s);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -166,15 +362,49 @@ extern "C" int sdrm_cu_interp_fir(const sdrm_interp_args *a, void *stream_ptr) {
     cudaStream_t stream = (cudaStream_t) stream_ptr;
     const long long n_out = (long long) a->n_in * a->interpolation;
     if (n_out > 0) {
-        long long bx = (n_out + 255) / 256;
-        if (bx > 2048) {
-            bx = 2048;
-        }
-        dim3 grid((unsigned) bx, (unsigned) a->n_ch);
-        if (a->in_is_bytes) {
-            interp_shape_kernel<true><<<grid, 256, 0, stream>>>(*a);
+        if (a->out_grouped) {
+            long long bx = ((long long) a->n_in + 7) / 8;
+            if (bx > 1024) {
+                bx = 1024;
+            }
+            dim3 grid((unsigned) bx, (unsigned) ((a->n_ch + 31) / 32));
+            if (a->in_is_bytes) {
+                if (a->branch_taps <= 8 && a->interpolation <= 32) {
+                    long long wx = (((long long) a->n_in + 31) / 32 + 7) / 8;
+                    const long long want = (148LL * 8 + grid.y - 1) / grid.y;
+                    dim3 wgrid((unsigned) (wx < want ? wx : want), grid.y);
+                    bits_shape_kernel<<<wgrid, 256, 0, stream>>>(*a);
+                } else if (a->branch_taps <= 8) {
+                    interp_shape_kernel<true, true, 8><<<grid, 256, 0, stream>>>(*a);
+                } else {
+                    interp_shape_kernel<true, true, kMaxBranchTaps><<<grid, 256, 0, stream>>>(*a);
+                }
+            } else {
+                if (a->branch_taps <= 8) {
+                    interp_shape_kernel<false, true, 8><<<grid, 256, 0, stream>>>(*a);
+                } else {
+                    interp_shape_kernel<false, true, kMaxBranchTaps><<<grid, 256, 0, stream>>>(*a);
+                }
+            }
         } else {
-            interp_shape_kernel<false><<<grid, 256, 0, stream>>>(*a);
+            long long bx = ((long long) a->n_in + 255) / 256;
+            if (bx > 2048) {
+                bx = 2048;
+            }
+            dim3 grid((unsigned) bx, (unsigned) a->n_ch);
+            if (a->in_is_bytes) {
+                if (a->branch_taps <= 8) {
+                    interp_shape_kernel<true, false, 8><<<grid, 256, 0, stream>>>(*a);
+                } else {
+                    interp_shape_kernel<true, false, kMaxBranchTaps><<<grid, 256, 0, stream>>>(*a);
+                }
+            } else {
+                if (a->branch_taps <= 8) {
+                    interp_shape_kernel<false, false, 8><<<grid, 256, 0, stream>>>(*a);
+                } else {
+                    interp_shape_kernel<false, false, kMaxBranchTaps><<<grid, 256, 0, stream>>>(*a);
+                }
+            }
         }
     }
     if (a->branch_taps > 1) {
@@ -188,22 +418,29 @@ extern "C" int sdrm_cu_interp_fir(const sdrm_interp_args *a, void *stream_ptr) {
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }
 
-extern "C" int sdrm_cu_freq_mod(const float *increments, float *phases, size_t stride, float *phase_state, void *out,
-                                size_t out_stride, long long n, int n_ch, void *stream_ptr) {
+extern "C" int sdrm_cu_freq_mod(float *work, size_t rows, float *phase_state, void *out, size_t out_stride, long long n, int n_ch,
+                                void *stream_ptr) {
     if (n <= 0 || n_ch <= 0) {
         return 0;
     }
-    if ((stride & 3) != 0) {
+    if ((long long) rows < n || ((uintptr_t) work & 127) != 0) {
         return -22;
     }
     cudaStream_t stream = (cudaStream_t) stream_ptr;
-    phase_walk_kernel<<<(n_ch + 31) / 32, 32, 0, stream>>>(increments, phases, stride, phase_state, (int) n, n_ch);
-    long long bx = (n + 255) / 256;
-    if (bx > 1024) {
-        bx = 1024;
+    const int groups = (n_ch + 31) / 32;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(phase_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem);
+        configured = true;
     }
-    dim3 grid((unsigned) bx, (unsigned) n_ch);
-    phase_to_iq_kernel<<<grid, 256, 0, stream>>>(phases, stride, (float2 *) out, out_stride, n);
+    phase_walk_kernel<<<groups, 32, kWalkSmem, stream>>>(work, rows, phase_state, n, n_ch);
+    long long bx = (n + kTileRows - 1) / kTileRows;
+    const long long want = (148LL * 8 + groups - 1) / groups;
+    if (bx > want) {
+        bx = want;
+    }
+    dim3 grid((unsigned) bx, (unsigned) groups);
+    phase_to_iq_kernel<<<grid, 256, 0, stream>>>(work, rows, (float2 *) out, out_stride, n, n_ch);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }

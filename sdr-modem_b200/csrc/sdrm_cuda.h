@@ -202,19 +202,20 @@ typedef struct {
     int apply_scale;
     float scale;
     float *out;
-    size_t out_stride;
+    size_t out_stride; /* floats per row; with out_grouped: time steps per group (rows of the GTC layout) */
+    int out_grouped;   /* 0: out[ch][m]; 1: GTC layout out[ch / 32][m][ch % 32], the input of sdrm_cu_freq_mod */
 } sdrm_interp_args;
 
 int sdrm_cu_interp_fir(const sdrm_interp_args *args, void *stream);
 
 /*
- * Frequency modulator (reference src/dsp/frequency_modulator.c:41-60): phase = wrap(phase + increments[m]) in float,
- * out[m] = cos(phase) + j sin(phase) evaluated in double and rounded to float. increments already hold
- * sensitivity * input. increments / phases: float [n_ch][stride] (stride % 4 == 0); phases is scratch and may alias
- * increments. out: float2 rows.
+ * Frequency modulator (reference src/dsp/frequency_modulator.c:41-60): phase = wrap(phase + work[m]) in float, in place,
+ * then out[ch][m] = cos(phase) + j sin(phase) evaluated in double and rounded to float. `work` holds
+ * sensitivity * input in the GTC layout float [ceil(n_ch / 32)][rows][32] (128-byte aligned, rows >= n) and is
+ * overwritten with the phases. out: float2 rows.
  */
-int sdrm_cu_freq_mod(const float *increments, float *phases, size_t stride, float *phase_state, void *out,
-                     size_t out_stride, long long n, int n_ch, void *stream);
+int sdrm_cu_freq_mod(float *work, size_t rows, float *phase_state, void *out, size_t out_stride, long long n, int n_ch,
+                     void *stream);
 
 #ifdef __cplusplus
 }

@@ -69,8 +69,9 @@ struct sdrm_gfsk_mod_batch_t {
     float *d_taps_rev;
     float *d_history; /* [n_ch][branch_taps - 1] */
     float *d_phase;   /* [n_ch] */
-    float *d_work;    /* [n_ch][work_stride]: increments, then phases, in place */
-    size_t work_stride;
+    float *d_work;    /* GTC layout [groups][work_rows][32]: increments, then phases, in place */
+    size_t work_rows;
+    uint32_t n_groups;
     void *d_in;
     size_t in_stride_dev;
     void *d_out;
@@ -123,10 +124,11 @@ int sdrm_gfsk_mod_batch_create(uint32_t n_channels, float samples_per_symbol, fl
     free(square);
     free(taps);
     const size_t max_out = (size_t) max_input_buffer_length * 8 * (size_t) b->interpolation;
-    b->work_stride = sdrm_round_up(max_out, 4) + 4;
+    b->work_rows = sdrm_round_up(max_out, 32) + 32;
+    b->n_groups = (n_channels + 31) / 32;
     if (code == 0) code = sdrm_dev_zalloc((void **) &b->d_history, (size_t) n_channels * (b->branch_taps > 1 ? b->branch_taps - 1 : 1) * sizeof(float));
     if (code == 0) code = sdrm_dev_zalloc((void **) &b->d_phase, n_channels * sizeof(float));
-    if (code == 0) code = sdrm_dev_zalloc((void **) &b->d_work, (size_t) n_channels * b->work_stride * sizeof(float));
+    if (code == 0) code = sdrm_dev_zalloc((void **) &b->d_work, (size_t) b->n_groups * b->work_rows * 32 * sizeof(float));
     if (code == 0) code = sdrm_cuda_code(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "stream");
     if (code != 0) {
         sdrm_gfsk_mod_batch_destroy(b);
@@ -151,12 +153,12 @@ static int mod_enqueue(sdrm_gfsk_mod_batch *b, const void *d_in, size_t in_strid
     a.apply_scale = 1;
     a.scale = b->sensitivity;
     a.out = b->d_work;
-    a.out_stride = b->work_stride;
+    a.out_stride = b->work_rows;
+    a.out_grouped = 1;
     int code = sdrm_launch_code(sdrm_cu_interp_fir(&a, b->stream), "gfsk shaping");
     if (code != 0) return code;
     const long long n_out = (long long) n_bytes * 8 * b->interpolation;
-    code = sdrm_launch_code(sdrm_cu_freq_mod(b->d_work, b->d_work, b->work_stride, b->d_phase, d_out, out_stride, n_out, (int) b->n_ch,
-                                             b->stream),
+    code = sdrm_launch_code(sdrm_cu_freq_mod(b->d_work, b->work_rows, b->d_phase, d_out, out_stride, n_out, (int) b->n_ch, b->stream),
                             "frequency modulator");
     b->launches += 4;
     return code;
@@ -418,13 +420,13 @@ int frequency_modulator_create(float sensitivity, uint32_t max_input_buffer_leng
     }
     m->sensitivity = sensitivity;
     m->max_len = max_input_buffer_length;
-    const size_t cap = sdrm_round_up((size_t) max_input_buffer_length, 4) + 4;
-    int code = sdrm_dev_zalloc((void **) &m->d_work, cap * sizeof(float));
+    const size_t cap = sdrm_round_up((size_t) max_input_buffer_length, 32) + 32;
+    int code = sdrm_dev_zalloc((void **) &m->d_work, cap * 32 * sizeof(float));
     if (code == 0) code = sdrm_dev_zalloc((void **) &m->d_phase, sizeof(float));
     if (code == 0) code = sdrm_dev_zalloc(&m->d_out, cap * 8);
     if (code == 0) code = sdrm_cuda_code(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking), "stream");
     if (code == 0) {
-        m->h_scaled = malloc(cap * sizeof(float));
+        m->h_scaled = calloc(cap * 32, sizeof(float));
         m->output = malloc(cap * sizeof(float complex));
         if (m->h_scaled == NULL || m->output == NULL) {
             code = -ENOMEM;
@@ -450,12 +452,13 @@ void frequency_modulator_process(float *input, size_t input_len, float complex *
         return;
     }
     /* sensitivity * input[i], rounded to float before it is added to the phase (frequency_modulator.c:49) */
+    /* one stream rides in lane 0 of a channel group (GTC layout [time][32]) */
     for (size_t i = 0; i < input_len; i++) {
-        m->h_scaled[i] = m->sensitivity * input[i];
+        m->h_scaled[i * 32] = m->sensitivity * input[i];
     }
-    const size_t cap = sdrm_round_up((size_t) m->max_len, 4) + 4;
-    int ok = cudaMemcpyAsync(m->d_work, m->h_scaled, input_len * sizeof(float), cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
-    ok = ok && sdrm_launch_code(sdrm_cu_freq_mod(m->d_work, m->d_work, cap, m->d_phase, m->d_out, cap, (long long) input_len, 1, m->stream),
+    const size_t cap = sdrm_round_up((size_t) m->max_len, 32) + 32;
+    int ok = cudaMemcpyAsync(m->d_work, m->h_scaled, input_len * 32 * sizeof(float), cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
+    ok = ok && sdrm_launch_code(sdrm_cu_freq_mod(m->d_work, cap, m->d_phase, m->d_out, cap, (long long) input_len, 1, m->stream),
                                 "frequency modulator") == 0;
     ok = ok && cudaMemcpyAsync(m->output, m->d_out, input_len * 8, cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
     ok = ok && sdrm_cuda_code(cudaStreamSynchronize(m->stream), "frequency_modulator_process") == 0;

@@ -1,0 +1,180 @@
+#!/usr/bin/env python3
+"""Secondary benchmark lines (not the driver's contract; that is bench.py = BASELINE configs[1]):
+
+  python tools/bench_configs.py --config c4 [--channels 1024]   gfsk_mod batch, 2048-byte packets, sps 2 (configs[3])
+  python tools/bench_configs.py --config c3 [--channels 4096]   doppler + GMSK 2400 baud from 2.4 Msps, decim 100 (configs[2])
+
+Each prints one JSON line with the device-resident throughput, the roofline that bounds the stage, and the reference's
+CPU chain (oracle/_ref) timed on the host cores for a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "sdr-modem_b200"))
+
+LUCKY7_TLE = ["LUCKY-7",
+              "1 44406U 19038W   20069.88080907  .00000505  00000-0  32890-4 0  9992",
+              "2 44406  97.5270  32.5584 0026284 107.4758 252.9348 15.12089395 37524"]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def bench_c4(args):
+    import torch
+    import sdrm
+    from oracle import ref
+    import workloads
+    n_ch, packet = args.channels, 2048
+    sps, sens = 2.0, float(np.float32(2 * np.pi * 5000 / 19200))
+    out_per_packet = packet * 8 * int(sps)
+    mod = sdrm.GfskModBatch(n_ch, sps, sens, 0.5, packet, device=0)
+    rng = np.random.default_rng(2000)
+    data = torch.from_numpy(rng.integers(0, 256, (2, n_ch, packet), dtype=np.uint8)).cuda()
+    out = torch.empty((2, n_ch, out_per_packet), dtype=torch.complex64, device="cuda")
+    stream = torch.cuda.ExternalStream(mod.stream)
+
+    def step(k):
+        mod.process_device(data[k % 2].data_ptr(), packet, packet, out[k % 2].data_ptr(), out_per_packet)
+
+    for k in range(args.warmup):
+        step(k)
+    mod.sync()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(stream)
+    for k in range(args.steps):
+        step(k)
+    end.record(stream)
+    mod.sync()
+    ms = start.elapsed_time(end) / args.steps
+    samples = n_ch * out_per_packet
+    value = samples / (ms * 1e-3) / 1e6
+    pk, kind = peaks()
+    bytes_per_sample = 8 + 1.0 / (8 * sps)
+    achieved = value * 1e6 * bytes_per_sample / 1e9
+    cores = os.cpu_count() or 1
+    cpu_data = rng.integers(0, 256, (cores, packet), dtype=np.uint8)
+    sec, cnt = ref.bench_gfsk_mod(sps, sens, 0.5, cpu_data, cores, packets=200)
+    print(json.dumps({
+        "metric": "modulated Msamples/s (output)", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d channels x %d-byte packets, gfsk_mod sps 2, BT 0.5 (BASELINE configs[3])" % (n_ch, packet),
+                   "l2": "2 x %.0f MB output buffers rotating" % (samples * 8 / 1e6)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                     "note": "8.06 algorithmic B per output sample; the float phase recurrence (one lane per channel, ~14 cycles "
+                             "per sample) bounds batches below a few thousand channels"},
+        "cpu_baseline": {"value": cnt / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                         "sample": "%d channels x 200 packets of %d bytes" % (cores, packet)},
+        "gpu_launches": int(mod.launch_count)}))
+
+
+def bench_c3(args):
+    import torch
+    import sdrm
+    from oracle import ref
+    import workloads
+    n_ch, chunk = args.channels, 131072
+    shape = workloads.DemodShape("gmsk2400@2.4M/chunk131072", 2400000, 2400, 5000, 100, 2000, True, chunk)
+    flops, t1, t2 = workloads.demod_flops_per_sample(shape)
+    lat, lon = float(np.float32(53.72)), float(np.float32(47.57))
+    channels = [sdrm.doppler_channel(lat, lon, 0.0, 0, 1583840449 + c, LUCKY7_TLE) for c in range(n_ch)]
+    dop = sdrm.DopplerBatch(channels, shape.sampling_freq, 437525000, chunk, device=0)
+    cap = int(chunk / 100 / 10 * 1.2) + 64
+    demod = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=cap, device=0)
+    t0 = time.time()
+    iq = workloads.gfsk_channels(n_ch, 2 * chunk, shape, seed=3000, device="cuda", max_offset_hz=4000.0)
+    bufs = [iq[:, i * chunk:(i + 1) * chunk].contiguous() for i in range(2)]
+    del iq
+    corrected = torch.empty((n_ch, chunk), dtype=torch.complex64, device="cuda")
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+    dop_stream = torch.cuda.ExternalStream(dop.stream)
+    fir_stream = torch.cuda.ExternalStream(demod.stream)
+    tail_stream = torch.cuda.ExternalStream(demod.tail_stream)
+    ev = torch.cuda.Event()
+
+    def step(k):
+        # the doppler output buffer is reused every step: wait until the previous call's filters have consumed it
+        dop_stream.wait_stream(fir_stream)
+        dop.process_device(bufs[k % 2].data_ptr(), chunk, chunk, corrected.data_ptr(), chunk, direction=1)
+        ev.record(dop_stream)
+        fir_stream.wait_event(ev)
+        demod.process_device(corrected.data_ptr(), chunk, chunk)
+        demod.release()
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(dop_stream)
+    for k in range(args.steps):
+        step(k)
+    end.record(tail_stream)
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / args.steps
+    value = n_ch * chunk / (ms * 1e-3) / 1e6
+    demod.set_profiling(True)
+    step(0)
+    stage = demod.stage_times()
+    pk, kind = peaks()
+    peak = 148 * 128 * 2 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+    achieved = value * 1e6 * flops / 1e12
+    cores = os.cpu_count() or 1
+    cpu = None
+    if not args.no_cpu:
+        x = workloads.gfsk_channels(cores, chunk, shape, seed=3000, device="cpu", max_offset_hz=4000.0).numpy()
+        t0 = time.time()
+        # the reference's dsp_worker chain: doppler_process_rx -> fsk_demod_process, one channel per core (threads via processes)
+        import concurrent.futures as cf
+
+        def one(c):
+            d = ref.doppler(lat, lon, 0.0, shape.sampling_freq, 437525000, 0, 1583840449 + c, chunk, LUCKY7_TLE)
+            f = ref.fsk_demod(*shape.create_args, chunk)
+            return len(f.process(d.process(x[c])))
+        with cf.ThreadPoolExecutor(cores) as pool:  # ctypes releases the GIL inside the reference's C code
+            list(pool.map(one, range(cores)))
+        sec = time.time() - t0
+        cpu = {"value": cores * chunk / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+               "sample": "%d channels x %d samples (one call each), doppler_process_rx + fsk_demod_process" % (cores, chunk)}
+    print(json.dumps({
+        "metric": "demodulated Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d channels x doppler + %s, decim 100, dc on (BASELINE configs[2]); T1 = %d, T2 = %d"
+                               % (n_ch, shape.name, t1, t2), "mode": "exact", "input_gen_s": gen_s,
+                   "flop_per_sample": flops},
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "stage_ms": {"lpf1_quad": stage[0], "lpf2": stage[1], "dc_clock_tail": stage[2]}},
+        "cpu_baseline": cpu, "error_flags": demod.error_flags()}))
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--config", required=True, choices=["c3", "c4"])
+    p.add_argument("--channels", type=int, default=None)
+    p.add_argument("--steps", type=int, default=None)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--no-cpu", action="store_true")
+    args = p.parse_args()
+    if args.config == "c4":
+        args.channels = args.channels or 1024
+        args.steps = args.steps or 50
+        bench_c4(args)
+    else:
+        args.channels = args.channels or 4096
+        args.steps = args.steps or 3
+        bench_c3(args)
+
+
+if __name__ == "__main__":
+    main()
