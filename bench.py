@@ -33,7 +33,7 @@ UNIT = "Msamples/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--channels", type=int, default=1024, help="channels per GPU")
@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -70,9 +70,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=10.0):
+        """nvidia-smi takes a while to start; the timed region should not begin before it delivers"""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,7 +87,9 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, sm_max, power, reasons = [], [], [], set()
-        for line in self.lines:
+        for stamp, line in self.lines:
+            if t_begin is not None and not (t_begin <= stamp <= t_end):
+                continue  # only samples taken while the timed region was running
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 8:
                 continue
@@ -141,26 +149,39 @@ def cpu_reference_run(shape, seconds, n_threads=None):
 
 
 def run_reference_arm(args, shape):
+    """bench.py --impl reference: the reference's own CPU chain (oracle/_ref, built from the reference sources in place) on all
+    host cores, same metric and workload shape; a step is a bounded sample (a few passes of 16 x 2 chunks), so that
+    K steps + W warm-ups end within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps_vals = []
-    base = None
+    from oracle import ref
+    import workloads
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsdrmodem_ref.so not built"}))
+        return
+    cores = os.cpu_count() or 1
+    n = shape.chunk * 2
+    iq = workloads.gfsk_channels(cores, n, shape, seed=1000, device="cpu").numpy()
+    sec, _ = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=1)
+    target = max(0.2, args.cpu_seconds / max(1, args.steps))
+    passes = max(1, int(round(target / max(sec, 1e-3))))
     for _ in range(args.warmup):
-        cpu_reference_run(shape, 0.5)
+        ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=1)
+    total_sec, total_samples = 0.0, 0
     for _ in range(args.steps):
-        base = cpu_reference_run(shape, max(1.0, args.cpu_seconds / max(1, args.steps)))
-        if base is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsdrmodem_ref.so not built"}))
-            return
-        steps_vals.append(base["value"])
-    value = float(np.mean(steps_vals))
-    base["value"] = value
+        sec, _ = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=passes)
+        total_sec += sec
+        total_samples += cores * n * passes
+    value = total_samples / total_sec / 1e6
+    sample = ("%d channels x %d samples x %d passes per step, chunk %d, oracle/_ref strict build (-O2 -ffp-contract=off, VOLK "
+              "generic shim), one thread per channel" % (cores, n, passes, shape.chunk))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * base["seconds"], "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * total_sec / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": shape.name, "channels": base["cores"], "chunk": shape.chunk},
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": "%d channels x %s, GMSK BT 0.5, Eb/N0 12 dB, dev 5 kHz, decim 2, dc on (BASELINE configs[1], "
+                                   "bounded sample)" % (cores, shape.name), "channels": cores, "chunk": shape.chunk},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -212,20 +233,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
-        step(k)
-    barrier()
-    launches_before = batch.launch_count
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for k in range(args.warmup):
+        step(k)
+    sampler.wait_first_sample()
+    barrier()
+    launches_before = batch.launch_count
     start = torch.cuda.Event(enable_timing=True)
     end = torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     start.record(fir_stream)
     for k in range(args.steps):
         step(args.warmup + k)
     end.record(tail_stream)
     barrier()
-    clocks = sampler.stop()
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end)
     ms_total = start.elapsed_time(end)
     launches = int(batch.launch_count - launches_before)
 

@@ -16,6 +16,7 @@
 #include "../../include/sdrm/clock_recovery_mm.h"
 #include "../../include/sdrm/dc_blocker.h"
 #include "../../include/sdrm/fast_atan2f.h"
+#include "../../include/sdrm/fir_filter.h"
 #include "../../include/sdrm/lpf.h"
 #include "../../include/sdrm/lpf_taps.h"
 #include "../../include/sdrm/quadrature_demod.h"
@@ -62,9 +63,10 @@ float fast_atan2f(float y, float x) {
     return x >= 0.0f ? -1.57079632679489661923F + base : -1.57079632679489661923F - base;
 }
 
-/* ------------------------------------------------------------------------------------------------ lpf */
+/* ------------------------------------------------------------------------------------------------ fir_filter / lpf */
 
-struct lpf_t {
+/* One streaming decimating FIR over one stream (reference fir_filter.c:35-159): shared by fir_filter_* and lpf_*. */
+struct fir_core {
     uint8_t decimation;
     size_t num_bytes;
     size_t max_len;
@@ -81,33 +83,37 @@ struct lpf_t {
     cudaStream_t stream;
 };
 
-int lpf_create(uint8_t decimation, uint64_t sampling_freq, uint64_t cutoff_freq, uint32_t transition_width,
-               size_t max_input_buffer_length, size_t num_bytes, lpf **filter) {
-    if (decimation == 0 || (num_bytes != 8 && num_bytes != 4)) {
+static void fir_core_free(struct fir_core *f) {
+    if (f->stream != NULL) {
+        cudaStreamSynchronize(f->stream);
+        cudaStreamDestroy(f->stream);
+    }
+    cudaFree(f->d_taps);
+    cudaFree(f->d_hist[0]);
+    cudaFree(f->d_hist[1]);
+    cudaFree(f->d_in);
+    cudaFree(f->d_out);
+    free(f->h_pack);
+    free(f->output);
+    memset(f, 0, sizeof(*f));
+}
+
+/* taps in design order (h[0] multiplies the newest sample), not consumed */
+static int fir_core_init(struct fir_core *f, uint8_t decimation, const float *taps, size_t taps_len, size_t max_len,
+                         size_t num_bytes) {
+    if (decimation == 0 || taps_len == 0 || (num_bytes != 8 && num_bytes != 4)) {
         return -1;
-    }
-    struct lpf_t *f = calloc(1, sizeof(*f));
-    if (f == NULL) {
-        return -ENOMEM;
-    }
-    float *taps = NULL;
-    size_t taps_len = 0;
-    int code = sdrm_design_low_pass(1.0F, sampling_freq, cutoff_freq, transition_width, &taps, &taps_len);
-    if (code != 0) {
-        lpf_destroy(f);
-        return code;
     }
     f->decimation = decimation;
     f->num_bytes = num_bytes;
-    f->max_len = max_input_buffer_length;
+    f->max_len = max_len;
     f->n_taps = (int) taps_len;
     f->hist_len = (int) sdrm_round_up(taps_len - 1, 2);
     if (f->hist_len == 0) {
         f->hist_len = 2;
     }
-    code = sdrm_upload_taps_dup(taps, taps_len, &f->d_taps);
-    free(taps);
-    const size_t cap = sdrm_round_up(max_input_buffer_length, 2) + 2;
+    int code = sdrm_upload_taps_dup(taps, taps_len, &f->d_taps);
+    const size_t cap = sdrm_round_up(max_len, 2) + 2;
     for (int i = 0; i < 2 && code == 0; i++) {
         code = sdrm_dev_zalloc(&f->d_hist[i], (size_t) f->hist_len * 8);
     }
@@ -121,15 +127,10 @@ int lpf_create(uint8_t decimation, uint64_t sampling_freq, uint64_t cutoff_freq,
             code = -ENOMEM;
         }
     }
-    if (code != 0) {
-        lpf_destroy(f);
-        return code;
-    }
-    *filter = f;
-    return 0;
+    return code;
 }
 
-void lpf_process(const void *input, size_t input_len, void **output, size_t *output_len, lpf *f) {
+static void fir_core_process(struct fir_core *f, const void *input, size_t input_len, void **output, size_t *output_len) {
     *output = NULL;
     *output_len = 0;
     if (input_len > f->max_len) {
@@ -168,12 +169,12 @@ void lpf_process(const void *input, size_t input_len, void **output, size_t *out
     a.out_mode = SDRM_FIR_OUT_ROWS;
     a.out = f->d_out;
     a.out_stride = a.in_stride;
-    if (sdrm_launch_code(sdrm_cu_fir(&a, f->stream), "lpf") != 0) {
+    if (sdrm_launch_code(sdrm_cu_fir(&a, f->stream), "fir") != 0) {
         return;
     }
     if (sdrm_launch_code(sdrm_cu_hist_update(f->d_in, a.in_stride, f->d_hist[f->cur], f->d_hist[f->cur ^ 1], f->hist_len, n_in, 1,
                                              f->stream),
-                         "lpf history") != 0) {
+                         "fir history") != 0) {
         return;
     }
     f->cur ^= 1;
@@ -182,7 +183,7 @@ void lpf_process(const void *input, size_t input_len, void **output, size_t *out
     if (n_out > 0 && cudaMemcpyAsync(dst, f->d_out, (size_t) n_out * 8, cudaMemcpyDeviceToHost, f->stream) != cudaSuccess) {
         return;
     }
-    if (sdrm_cuda_code(cudaStreamSynchronize(f->stream), "lpf_process") != 0) {
+    if (sdrm_cuda_code(cudaStreamSynchronize(f->stream), "fir_process") != 0) {
         return;
     }
     if (f->num_bytes == 4) {
@@ -195,21 +196,112 @@ void lpf_process(const void *input, size_t input_len, void **output, size_t *out
     *output_len = (size_t) n_out;
 }
 
+/* fir_filter: reference src/dsp/fir_filter.h:29-35. The struct is opaque here (the reference's fields describe its
+ * host working buffers; nothing outside src/dsp reads them). */
+struct fir_filter_t {
+    struct fir_core core;
+    float *taps;     /* the caller's malloc: owned from a successful create on, as in fir_filter.c:58,171-173 */
+    float *reversed; /* taps_len floats, reversed (fir_filter.c:27), for fir_filter_process_float_single */
+    size_t taps_len;
+};
+
+int fir_filter_create(uint8_t decimation, float *taps, size_t taps_len, size_t max_input_buffer_length, size_t num_bytes,
+                      fir_filter **filter) {
+    if (taps == NULL) {
+        return -1;
+    }
+    struct fir_filter_t *f = calloc(1, sizeof(*f));
+    if (f == NULL) {
+        return -ENOMEM;
+    }
+    /* from here on the filter owns the taps, also when create fails (fir_filter.c:58 followed by fir_filter_destroy) */
+    f->taps = taps;
+    f->taps_len = taps_len;
+    int code = fir_core_init(&f->core, decimation, taps, taps_len, max_input_buffer_length, num_bytes);
+    if (code == 0) {
+        f->reversed = malloc(sizeof(float) * taps_len);
+        if (f->reversed == NULL) {
+            code = -ENOMEM;
+        }
+    }
+    if (code != 0) {
+        fir_filter_destroy(f);
+        return code;
+    }
+    for (size_t i = 0; i < taps_len; i++) {
+        f->reversed[i] = taps[taps_len - 1 - i];
+    }
+    *filter = f;
+    return 0;
+}
+
+void fir_filter_process(const void *input, size_t input_len, void **output, size_t *output_len, fir_filter *filter) {
+    fir_core_process(&filter->core, input, input_len, output, output_len);
+}
+
+/* One output from taps_len host floats, no state (fir_filter.c:116-121). The reference rounds the pointer down to its
+ * 16-byte alignment and runs the dot product over (input - k .. input + taps_len) with k leading zero taps; the zeros
+ * only matter when a sample in front of `input` is not finite, and that case is kept. */
+float fir_filter_process_float_single(const float *input, fir_filter *filter) {
+    const size_t lead = ((size_t) input & 15u) / sizeof(float);
+    const float *p = input - lead;
+    float acc = 0.0f;
+    for (size_t i = 0; i < lead; i++) {
+        acc += p[i] * 0.0f;
+    }
+    for (size_t i = 0; i < filter->taps_len; i++) {
+        acc += input[i] * filter->reversed[i];
+    }
+    return acc;
+}
+
+void fir_filter_destroy(fir_filter *filter) {
+    if (filter == NULL) {
+        return;
+    }
+    fir_core_free(&filter->core);
+    free(filter->taps);
+    free(filter->reversed);
+    free(filter);
+}
+
+struct lpf_t {
+    struct fir_core core;
+};
+
+int lpf_create(uint8_t decimation, uint64_t sampling_freq, uint64_t cutoff_freq, uint32_t transition_width,
+               size_t max_input_buffer_length, size_t num_bytes, lpf **filter) {
+    if (decimation == 0 || (num_bytes != 8 && num_bytes != 4)) {
+        return -1;
+    }
+    struct lpf_t *f = calloc(1, sizeof(*f));
+    if (f == NULL) {
+        return -ENOMEM;
+    }
+    float *taps = NULL;
+    size_t taps_len = 0;
+    int code = sdrm_design_low_pass(1.0F, sampling_freq, cutoff_freq, transition_width, &taps, &taps_len);
+    if (code == 0) {
+        code = fir_core_init(&f->core, decimation, taps, taps_len, max_input_buffer_length, num_bytes);
+        free(taps);
+    }
+    if (code != 0) {
+        lpf_destroy(f);
+        return code;
+    }
+    *filter = f;
+    return 0;
+}
+
+void lpf_process(const void *input, size_t input_len, void **output, size_t *output_len, lpf *f) {
+    fir_core_process(&f->core, input, input_len, output, output_len);
+}
+
 void lpf_destroy(lpf *f) {
     if (f == NULL) {
         return;
     }
-    if (f->stream != NULL) {
-        cudaStreamSynchronize(f->stream);
-        cudaStreamDestroy(f->stream);
-    }
-    cudaFree(f->d_taps);
-    cudaFree(f->d_hist[0]);
-    cudaFree(f->d_hist[1]);
-    cudaFree(f->d_in);
-    cudaFree(f->d_out);
-    free(f->h_pack);
-    free(f->output);
+    fir_core_free(&f->core);
     free(f);
 }
 

@@ -106,6 +106,48 @@ def test_lpf_bit_exact(sdrm, port, dec, cplx, chunk):
     assert same_bits(y, port.Fir(port.low_pass_taps(1.0, 48000, 4800, 2000), dec, cplx).run(x, chunk))
 
 
+def make_fir(lib, dec, taps, max_len, cplx):
+    """fir_filter_create takes ownership of a malloc'ed taps array"""
+    libc = C.CDLL(None)
+    libc.malloc.restype = VP
+    libc.malloc.argtypes = [SZ]
+    taps = np.ascontiguousarray(taps, np.float32)
+    mem = libc.malloc(taps.nbytes)
+    C.memmove(mem, taps.ctypes.data, taps.nbytes)
+    lib.fir_filter_create.argtypes = [C.c_uint8, VP, SZ, SZ, SZ, C.POINTER(VP)]
+    dt = np.complex64 if cplx else np.float32
+    return Block(lib, "fir_filter", (dec, mem, len(taps), max_len, 8 if cplx else 4), dt, dt)
+
+
+@pytest.mark.parametrize("dec,cplx,ntaps,chunk", [(1, True, 8, 500), (2, False, 33, 999), (4, True, 129, 1024), (1, False, 1, 100),
+                                                  (3, False, 600, 2048)])
+def test_fir_filter_bit_exact(sdrm, port, dec, cplx, ntaps, chunk):
+    """fir_filter handle with arbitrary taps (reference src/dsp/fir_filter.c), chunked, against the oracle"""
+    taps = noise(ntaps, 77)
+    x = noise(12000, 3, cplx)
+    f = make_fir(sdrm.lib, dec, taps, 2048, cplx)
+    y = f.run(x, chunk)
+    assert len(f.process(x[:4000])) == 0  # over max: NULL / 0, state untouched
+    f.close()
+    assert same_bits(y, port.Fir(taps, dec, cplx).run(x, chunk))
+
+
+def test_fir_filter_float_single(sdrm):
+    """fir_filter_process_float_single: one sequential dot product with the reversed taps (fir_filter.c:116-121)"""
+    taps = noise(8, 5)
+    f = make_fir(sdrm.lib, 1, taps, 64, False)
+    sdrm.lib.fir_filter_process_float_single.restype = C.c_float
+    sdrm.lib.fir_filter_process_float_single.argtypes = [VP, VP]
+    x = noise(40, 6)
+    for off in range(0, 12):
+        got = sdrm.lib.fir_filter_process_float_single(x[off:].ctypes.data_as(VP), f.h)
+        acc = np.float32(0)
+        for j in range(8):
+            acc = np.float32(acc + np.float32(x[off + j] * taps[7 - j]))
+        assert np.float32(got) == acc
+    f.close()
+
+
 def test_quadrature_demod(sdrm, port, kats):
     q = make_quad(sdrm.lib, 25.4, 2000)
     x = complex_ramp(200)
