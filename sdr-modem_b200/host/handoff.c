@@ -143,6 +143,14 @@ void take_buffer_for_processing(float complex **buffer, size_t *len, queue *q) {
     pthread_mutex_unlock(&q->mutex);
 }
 
+/* internal (rx_group.c): true when take_buffer_for_processing would not block */
+int sdrm_queue_has_data(queue *q) {
+    pthread_mutex_lock(&q->mutex);
+    const int result = q->filled > 0;
+    pthread_mutex_unlock(&q->mutex);
+    return result;
+}
+
 void complete_buffer_processing(queue *q) {
     pthread_mutex_lock(&q->mutex);
     q->detached = 0;

@@ -63,6 +63,10 @@ int sdrm_upload_mmse_table(float **d_table);
 const float *sdrm_host_atan_table(void);
 const float *sdrm_host_mmse_table(void);
 
+/* handoff.c: true when take_buffer_for_processing would not block */
+struct queue_t;
+int sdrm_queue_has_data(struct queue_t *q);
+
 static inline size_t sdrm_round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
 static inline uint32_t sdrm_next_pow2(uint64_t v) {

@@ -122,3 +122,130 @@ def test_worker_create_failures(sdrm, tmp_path):
     cfg = lucky7_config(tmp_path, 0)
     cfg.demod_baud_rate = 48000
     assert lib.sdrm_dsp_worker_create(1, -1, C.byref(cfg), C.byref(w)) == -1
+
+
+# ---- batched dispatcher: one queue / one thread / one set of launches for all sessions on an SDR stream -----------------
+
+SINK = C.CFUNCTYPE(None, VP, C.c_uint32, C.POINTER(C.c_int8), SZ)
+
+
+class RxSession(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("client_socket", C.c_int), ("sink", SINK), ("sink_ctx", VP), ("has_doppler", C.c_bool),
+                ("doppler_tle", (C.c_char * 80) * 3), ("doppler_latitude", C.c_int32), ("doppler_longitude", C.c_int32),
+                ("doppler_altitude", C.c_int32), ("file_start_time_seconds", C.c_int64)]
+
+
+class RxGroupConfig(C.Structure):
+    _fields_ = [("rx_center_freq", C.c_uint64), ("rx_sampling_freq", C.c_uint64), ("demod_baud_rate", C.c_uint32),
+                ("demod_decimation", C.c_uint32), ("demod_fsk_deviation", C.c_int64), ("demod_fsk_transition_width", C.c_uint32),
+                ("demod_fsk_use_dc_block", C.c_bool), ("buffer_size", C.c_uint32), ("queue_size", C.c_uint16),
+                ("blocking_queue", C.c_bool), ("device", C.c_int)]
+
+
+def setup_group(lib):
+    lib.sdrm_rx_group_create.argtypes = [C.POINTER(RxGroupConfig), C.POINTER(RxSession), C.c_uint32, C.POINTER(VP)]
+    lib.sdrm_rx_group_put.argtypes = [VP, SZ, VP]
+    lib.sdrm_rx_group_put.restype = None
+    lib.sdrm_rx_group_shutdown.argtypes = [VP]
+    lib.sdrm_rx_group_shutdown.restype = None
+    lib.sdrm_rx_group_blocks_done.argtypes = [VP]
+    lib.sdrm_rx_group_blocks_done.restype = C.c_uint64
+    lib.sdrm_rx_group_destroy.argtypes = [VP]
+    lib.sdrm_rx_group_destroy.restype = None
+
+
+def group_config(buffer_size):
+    cfg = RxGroupConfig()
+    cfg.rx_center_freq, cfg.rx_sampling_freq = 437525000, 48000
+    cfg.demod_baud_rate, cfg.demod_decimation, cfg.demod_fsk_deviation = 4800, 2, 5000
+    cfg.demod_fsk_transition_width, cfg.demod_fsk_use_dc_block = 2000, True
+    cfg.buffer_size, cfg.queue_size, cfg.blocking_queue, cfg.device = buffer_size, 8, True, -1
+    return cfg
+
+
+def test_rx_group_matches_independent_workers(sdrm, port):
+    """7 sessions on one SDR stream (5 with their own doppler start time, 2 without): every session must get exactly what an
+    independent doppler -> fsk_demod chain of the reference gives it (oracle/_ref doppler + oracle demod), block by block"""
+    from oracle import ref
+    lib = sdrm.lib
+    setup_group(lib)
+    raw = golden_array("lucky7.cf32", np.complex64)
+    chunk = 2000
+    starts = [1583840449, 1583840449 + 30, 1583840449 + 61, None, 1583840449 + 95, 1583840449 + 200, None]
+    collected = {i: [] for i in range(len(starts))}
+
+    def on_symbols(ctx, session_id, symbols, n):
+        collected[session_id].append(np.ctypeslib.as_array(symbols, shape=(n,)).copy())
+
+    sink = SINK(on_symbols)
+    sessions = (RxSession * len(starts))()
+    for i, start in enumerate(starts):
+        s = sessions[i]
+        s.id, s.client_socket, s.sink, s.sink_ctx = i, -1, sink, None
+        s.has_doppler = start is not None
+        for k, line in enumerate(LUCKY7_TLE):
+            rawline = line.encode("ascii")
+            C.memmove(C.addressof(s.doppler_tle[k]), rawline + b"\0", len(rawline) + 1)
+        s.doppler_latitude, s.doppler_longitude, s.doppler_altitude = 537200000, 475700000, 0
+        s.file_start_time_seconds = start or 0
+    cfg = group_config(chunk)
+    g = VP()
+    assert lib.sdrm_rx_group_create(C.byref(cfg), sessions, len(starts), C.byref(g)) == 0
+    n_blocks = 0
+    for o in range(0, len(raw), chunk):
+        part = np.ascontiguousarray(raw[o:o + chunk])
+        lib.sdrm_rx_group_put(part.ctypes.data_as(VP), len(part), g)
+        n_blocks += 1
+    lib.sdrm_rx_group_shutdown(g)
+    lib.sdrm_rx_group_destroy(g)  # joins the thread: queued blocks are processed first
+    lat, lon = 537200000 / 10E6, 475700000 / 10E6
+    for i, start in enumerate(starts):
+        x = raw
+        if start is not None:
+            d = ref.doppler(lat, lon, 0.0, 48000, 437525000, 0, start, chunk, LUCKY7_TLE)
+            x = np.concatenate([d.process(raw[o:o + chunk]) for o in range(0, len(raw), chunk)])
+        want, _ = port.FskDemod(48000, 4800, 5000, 2, 2000, True, chunk).run(x, chunk)
+        got = np.concatenate(collected[i]) if collected[i] else np.zeros(0, np.int8)
+        assert len(got) == len(want), "session %d" % i
+        # doppler trig is double cos/sin rounded to float: CUDA and glibc may differ in the last place once in ~1e8 samples
+        assert np.mean(got == want) > 0.9999 and np.abs(got.astype(int) - want.astype(int)).max() <= 1, "session %d" % i
+
+
+def test_rx_group_socket_and_failures(sdrm, port):
+    lib = sdrm.lib
+    setup_group(lib)
+    _, exp, args = FSK_GOLDENS["lucky7"]
+    iq = golden_array("lucky7.expected.cf32", np.complex64)
+    a, b = socket.socketpair()
+    sessions = (RxSession * 1)()
+    sessions[0].id, sessions[0].client_socket, sessions[0].has_doppler = 3, a.fileno(), False
+    cfg = group_config(4096)
+    g = VP()
+    assert lib.sdrm_rx_group_create(C.byref(cfg), sessions, 1, C.byref(g)) == 0
+    for o in range(0, len(iq), 4096):
+        part = np.ascontiguousarray(iq[o:o + 4096])
+        lib.sdrm_rx_group_put(part.ctypes.data_as(VP), len(part), g)
+    lib.sdrm_rx_group_destroy(g)
+    a.close()
+    chunks = []
+    while True:
+        data = b.recv(65536)
+        if not data:
+            break
+        chunks.append(data)
+    b.close()
+    got = np.frombuffer(b"".join(chunks), dtype=np.int8)
+    want, _ = port.FskDemod(*args, 4096).run(iq, 4096)
+    assert same_bits(got, want)
+    # create failures: bad TLE, cutoff above fs/2, queue size 0
+    sessions[0].has_doppler = True
+    bad = (LUCKY7_TLE[1][:-1] + "0").encode()
+    for k, line in enumerate([LUCKY7_TLE[0].encode(), bad, LUCKY7_TLE[2].encode()]):
+        C.memmove(C.addressof(sessions[0].doppler_tle[k]), line + b"\0", len(line) + 1)
+    assert lib.sdrm_rx_group_create(C.byref(cfg), sessions, 1, C.byref(g)) == -1
+    sessions[0].has_doppler = False
+    cfg.demod_baud_rate = 48000
+    assert lib.sdrm_rx_group_create(C.byref(cfg), sessions, 1, C.byref(g)) == -1
+    cfg = group_config(4096)
+    cfg.queue_size = 0
+    assert lib.sdrm_rx_group_create(C.byref(cfg), sessions, 1, C.byref(g)) == -1
