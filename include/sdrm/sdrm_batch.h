@@ -58,8 +58,16 @@ int sdrm_fsk_demod_batch_process(sdrm_fsk_demod_batch *batch, const float comple
  * host->device asynchronously (pinned memory recommended) and enqueues the chain, fetch (below) collects the oldest
  * call. process == submit + fetch.
  */
-#define SDRM_MAX_IN_FLIGHT 2
+#define SDRM_MAX_IN_FLIGHT 3
 int sdrm_fsk_demod_batch_submit(sdrm_fsk_demod_batch *batch, const float complex *input, size_t in_stride, size_t input_len);
+
+/*
+ * submit for int16 (I, Q) samples as the SDR delivers them: [channels][in_stride pairs]; converted on the device as the
+ * reference's PlutoSDR plugin does on the host, (float) v / scalar with scalar = 2048 (src/sdr/plutosdr.c:129). Half the
+ * host->device bytes of the cf32 call, same results as converting first.
+ */
+int sdrm_fsk_demod_batch_submit_i16(sdrm_fsk_demod_batch *batch, const int16_t *input, size_t in_stride, size_t input_len,
+                                    float scalar);
 
 /*
  * Device-resident variant: d_input is cf32 [channels][in_stride] in device memory (16-byte aligned, even stride).
@@ -163,6 +171,10 @@ int sdrm_gfsk_mod_batch_create(uint32_t n_channels, float samples_per_symbol, fl
 /* host buffers: input uint8 [channels][in_stride], output cf32 [channels][out_stride] */
 int sdrm_gfsk_mod_batch_process(sdrm_gfsk_mod_batch *batch, const uint8_t *input, size_t in_stride, size_t input_len,
                                 float complex *output, size_t out_stride, size_t *output_len);
+/* as process, followed on the device by the PlutoSDR egress conversion (src/sdr/plutosdr.c:83): int16 (I, Q) pairs
+ * [channels][out_stride pairs] = saturate(rint(v * scalar)), scalar = 32768 */
+int sdrm_gfsk_mod_batch_process_i16(sdrm_gfsk_mod_batch *batch, const uint8_t *input, size_t in_stride, size_t input_len,
+                                    int16_t *output, size_t out_stride, float scalar, size_t *output_len);
 /* device buffers, asynchronous on the batch's stream; d_output rows must be 8-byte aligned */
 int sdrm_gfsk_mod_batch_process_device(sdrm_gfsk_mod_batch *batch, const void *d_input, size_t in_stride, size_t input_len,
                                        void *d_output, size_t out_stride);
@@ -170,6 +182,15 @@ int sdrm_gfsk_mod_batch_sync(sdrm_gfsk_mod_batch *batch);
 void *sdrm_gfsk_mod_batch_stream(sdrm_gfsk_mod_batch *batch);
 uint64_t sdrm_gfsk_mod_batch_launch_count(const sdrm_gfsk_mod_batch *batch);
 void sdrm_gfsk_mod_batch_destroy(sdrm_gfsk_mod_batch *batch);
+
+/*
+ * SDR sample formats on device buffers (reference src/sdr/plutosdr.c:83,129; VOLK generic 16i <-> 32f kernels), rows of
+ * `len` complex samples, strides in complex samples, asynchronous on `stream` (a cudaStream_t, NULL = default stream).
+ */
+int sdrm_samples_i16_to_cf32_device(const void *d_input, size_t in_stride, void *d_output, size_t out_stride, float scalar,
+                                    size_t len, uint32_t rows, void *stream);
+int sdrm_samples_cf32_to_i16_device(const void *d_input, size_t in_stride, void *d_output, size_t out_stride, float scalar,
+                                    size_t len, uint32_t rows, void *stream);
 
 /* Pinned host memory for the host-buffer entry points (pageable memory works too, but copies serialise). */
 void *sdrm_pinned_alloc(size_t bytes);

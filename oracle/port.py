@@ -47,6 +47,8 @@ def load():
     lib.orc_clock_mm_process.argtypes = [vp, vp, sz, vp]
     lib.orc_clock_mm_destroy.argtypes = [vp]
     lib.orc_convert_8i.argtypes = [vp, C.c_float, sz, vp]
+    lib.orc_convert_16i_32f.argtypes = [vp, C.c_float, sz, vp]
+    lib.orc_convert_32f_16i.argtypes = [vp, C.c_float, sz, vp]
     lib.orc_fsk_demod_create.restype = vp
     lib.orc_fsk_demod_create.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_uint8, C.c_uint32, C.c_int, C.c_uint32]
     lib.orc_fsk_demod_process.restype = sz
@@ -105,6 +107,20 @@ def convolve(x, y):
     lib.orc_convolve(_p(x), len(x), _p(y), len(y), C.byref(p), C.byref(n))
     out = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
     lib.free(p)
+    return out
+
+
+def convert_16i_32f(x, scalar):
+    x = np.ascontiguousarray(x, dtype=np.int16)
+    out = np.empty(x.shape, np.float32)
+    load().orc_convert_16i_32f(_p(x), scalar, x.size, _p(out))
+    return out
+
+
+def convert_32f_16i(x, scalar):
+    x = _f32(x)
+    out = np.empty(x.shape, np.int16)
+    load().orc_convert_32f_16i(_p(x), scalar, x.size, _p(out))
     return out
 
 

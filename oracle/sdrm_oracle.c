@@ -445,6 +445,34 @@ void orc_convert_8i(const float *in, float scale, size_t n, int8_t *out) {
     }
 }
 
+/* VOLK volk_16i_s32f_convert_32f generic: out = (float) in / scalar. PlutoSDR ingest, reference src/sdr/plutosdr.c:129
+ * (scalar 2048). "parity unpinned" beyond the reference's own KAT (test/test_plutosdr.c:149-154): plutosdr.c needs libiio
+ * and is not part of oracle/_ref. */
+void orc_convert_16i_32f(const int16_t *in, float scalar, size_t n, float *out) {
+    for (size_t i = 0; i < n; i++) {
+        out[i] = (float) in[i] / scalar;
+    }
+}
+
+/* VOLK volk_32f_s32f_convert_16i generic: scale, saturate to [SHRT_MIN, SHRT_MAX], round half to even. PlutoSDR egress,
+ * reference src/sdr/plutosdr.c:83 (scalar 32768); KAT test/test_plutosdr.c:192-194. NaN (unspecified in C) gives 0, which is
+ * what the x86 conversion followed by the 16-bit truncation produces. */
+void orc_convert_32f_16i(const float *in, float scalar, size_t n, int16_t *out) {
+    for (size_t i = 0; i < n; i++) {
+        float r = in[i] * scalar;
+        if (r != r) {
+            out[i] = 0;
+            continue;
+        }
+        if (r > 32767.0f) {
+            r = 32767.0f;
+        } else if (r < -32768.0f) {
+            r = -32768.0f;
+        }
+        out[i] = (int16_t) rintf(r);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ fsk demod */
 
 struct orc_fsk_demod_t {

@@ -58,6 +58,10 @@ void orc_clock_mm_destroy(orc_clock_mm *c);
 /* --- float -> int8 (VOLK volk_32f_s32f_convert_8i generic, reference src/dsp/fsk_demod.c:106) --- */
 void orc_convert_8i(const float *in, float scale, size_t n, int8_t *out);
 
+/* --- SDR sample formats (VOLK generic 16i <-> 32f, reference src/sdr/plutosdr.c:83,129) --- */
+void orc_convert_16i_32f(const int16_t *in, float scalar, size_t n, float *out);
+void orc_convert_32f_16i(const float *in, float scalar, size_t n, int16_t *out);
+
 /* --- the whole chain (reference src/dsp/fsk_demod.c:28-110) --- */
 typedef struct orc_fsk_demod_t orc_fsk_demod;
 orc_fsk_demod *orc_fsk_demod_create(uint64_t fs, uint32_t baud, int64_t deviation, uint8_t decimation, uint32_t tw,

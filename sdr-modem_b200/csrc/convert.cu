@@ -1,0 +1,82 @@
+// SDR sample formats on the device (sm_100a): int16 IQ <-> cf32, so that the PCIe side of the chain carries 4 bytes per
+// complex sample instead of 8. Reference: the PlutoSDR plugin converts on the host with VOLK,
+//   RX  volk_16i_s32f_convert_32f(out, in, 2048.0F, n)      src/sdr/plutosdr.c:129   out = (float) in / scalar
+//   TX  volk_32f_s32f_convert_16i(out, in, 32768, n)        src/sdr/plutosdr.c:83    saturate, round half to even
+// Both are pure streaming passes bound by HBM (12 bytes per complex sample); rows are independent.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sdrm_cuda.h"
+
+namespace {
+
+// in: int16 (I, Q) pairs, row r at in + r * in_stride pairs; out: float2 rows. One thread per complex sample: the 4-byte
+// loads and 8-byte stores of a warp are contiguous.
+__global__ void i16_to_cf32_kernel(const short2 *__restrict__ in, size_t in_stride, float2 *__restrict__ out, size_t out_stride,
+                                   float scalar, int n) {
+    const short2 *x = in + (size_t) blockIdx.y * in_stride;
+    float2 *y = out + (size_t) blockIdx.y * out_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const short2 v = x[i];
+        y[i] = make_float2(__fdiv_rn((float) v.x, scalar), __fdiv_rn((float) v.y, scalar));
+    }
+}
+
+__device__ __forceinline__ short to_i16(float v, float scalar) {
+    float r = __fmul_rn(v, scalar);
+    if (r != r) {
+        return 0;
+    }
+    r = fminf(fmaxf(r, -32768.0f), 32767.0f);
+    return (short) __float2int_rn(r);
+}
+
+__global__ void cf32_to_i16_kernel(const float2 *__restrict__ in, size_t in_stride, short2 *__restrict__ out, size_t out_stride,
+                                   float scalar, int n) {
+    const float2 *x = in + (size_t) blockIdx.y * in_stride;
+    short2 *y = out + (size_t) blockIdx.y * out_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 v = x[i];
+        y[i] = make_short2(to_i16(v.x, scalar), to_i16(v.y, scalar));
+    }
+}
+
+dim3 convert_grid(int n, int rows) {
+    long long bx = ((long long) n + 255) / 256;
+    const long long want = (148LL * 16 + rows - 1) / rows;
+    if (bx > want) {
+        bx = want;
+    }
+    return dim3((unsigned) bx, (unsigned) rows);
+}
+
+}  // namespace
+
+extern "C" int sdrm_cu_i16_to_cf32(const void *in, size_t in_stride, void *out, size_t out_stride, float scalar, int n, int rows,
+                                   void *stream) {
+    if (n <= 0 || rows <= 0) {
+        return 0;
+    }
+    if (((uintptr_t) in & 3) != 0 || ((uintptr_t) out & 7) != 0) {
+        return -22;
+    }
+    i16_to_cf32_kernel<<<convert_grid(n, rows), 256, 0, (cudaStream_t) stream>>>((const short2 *) in, in_stride, (float2 *) out,
+                                                                                out_stride, scalar, n);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}
+
+extern "C" int sdrm_cu_cf32_to_i16(const void *in, size_t in_stride, void *out, size_t out_stride, float scalar, int n, int rows,
+                                   void *stream) {
+    if (n <= 0 || rows <= 0) {
+        return 0;
+    }
+    if (((uintptr_t) in & 7) != 0 || ((uintptr_t) out & 3) != 0) {
+        return -22;
+    }
+    cf32_to_i16_kernel<<<convert_grid(n, rows), 256, 0, (cudaStream_t) stream>>>((const float2 *) in, in_stride, (short2 *) out,
+                                                                                out_stride, scalar, n);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}

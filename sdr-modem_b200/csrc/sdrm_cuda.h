@@ -217,6 +217,15 @@ int sdrm_cu_interp_fir(const sdrm_interp_args *args, void *stream);
 int sdrm_cu_freq_mod(float *work, size_t rows, float *phase_state, void *out, size_t out_stride, long long n, int n_ch,
                      void *stream);
 
+/*
+ * SDR sample formats (reference src/sdr/plutosdr.c:83,129, VOLK generic kernels): int16 (I, Q) pairs <-> float2 rows.
+ * Strides in complex samples. i16 -> cf32: (float) v / scalar; cf32 -> i16: v * scalar, saturated, round half to even.
+ */
+int sdrm_cu_i16_to_cf32(const void *in, size_t in_stride, void *out, size_t out_stride, float scalar, int n, int rows,
+                        void *stream);
+int sdrm_cu_cf32_to_i16(const void *in, size_t in_stride, void *out, size_t out_stride, float scalar, int n, int rows,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,9 @@
 #define M_PI 3.14159265358979323846
 #endif
 
-#define SLOTS 2
+#define SLOTS 3
+/* the filters may run this many calls ahead of the serial tail; the lpf2 output ring is RING_LAG + 1 calls deep */
+#define RING_LAG 2
 
 struct sdrm_fsk_demod_batch_t {
     sdrm_fsk_demod_batch_config cfg;
@@ -85,6 +87,7 @@ struct sdrm_fsk_demod_batch_t {
 
     /* staging + results, one set per slot */
     void *d_in[SLOTS];
+    void *d_in16[SLOTS]; /* int16 staging of submit_i16 */
     size_t in_stride_dev;
     int8_t *d_hard[SLOTS];
     float *d_soft[SLOTS];
@@ -190,7 +193,7 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
     b->gain_mu = 0.5f / 8.0f;
     b->max_rows = max_len / config->decimation + 1;
     b->max_history = (int) (4.0f * sps) + 64;
-    b->ring_rows = sdrm_next_pow2((uint64_t) (SLOTS + 1) * b->max_rows + (uint64_t) b->max_history);
+    b->ring_rows = sdrm_next_pow2((uint64_t) (RING_LAG + 1) * b->max_rows + (uint64_t) b->max_history);
     b->tc_stride = b->n_ch_pad;
     code = sdrm_dev_zalloc((void **) &b->d_ring, (size_t) b->ring_rows * b->tc_stride * sizeof(float));
     if (code != 0) goto fail;
@@ -268,8 +271,15 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
         code = sdrm_cuda_code(cudaEventCreateWithFlags(&b->ev_done[s], cudaEventDisableTiming), "event");
         if (code != 0) goto fail;
     }
-    code = sdrm_cuda_code(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking), "stream");
-    if (code != 0) goto fail;
+    {
+        /* the copy stream also runs the int16 -> cf32 conversion of the NEXT call while this call's filters fill the GPU:
+         * its few blocks must not queue behind them */
+        int least = 0;
+        int greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        code = sdrm_cuda_code(cudaStreamCreateWithPriority(&b->s_copy, cudaStreamNonBlocking, greatest), "stream");
+        if (code != 0) goto fail;
+    }
     code = sdrm_cuda_code(cudaStreamCreateWithFlags(&b->s_fir, cudaStreamNonBlocking), "stream");
     if (code != 0) goto fail;
     code = sdrm_cuda_code(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking), "stream");
@@ -337,9 +347,9 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     const int dec = b->cfg.decimation;
     const int n_q = (int) n_in;
     const int n_rows = n_q > b->phase2 ? (n_q - b->phase2 + dec - 1) / dec : 0;
-    /* ring rows of call k - SLOTS are reused now: its tail must be done */
-    if (b->submitted >= SLOTS) {
-        SDRM_CUDA_TRY(cudaStreamWaitEvent(b->s_fir, b->ev_tail[slot], 0));
+    /* the ring rows written now were last needed by the tail of call k - RING_LAG (its look-back included) */
+    if (b->submitted >= RING_LAG) {
+        SDRM_CUDA_TRY(cudaStreamWaitEvent(b->s_fir, b->ev_tail[(b->submitted - RING_LAG) % SLOTS], 0));
     }
     sdrm_fir_args f2;
     memset(&f2, 0, sizeof(f2));
@@ -460,6 +470,12 @@ static int ensure_staging(sdrm_fsk_demod_batch *b, int slot) {
     return sdrm_dev_zalloc(&b->d_in[slot], (size_t) b->n_ch * b->in_stride_dev * 8);
 }
 
+/* host rows that can move with one linear copy: even stride (16-byte aligned device rows), little padding, fits staging */
+static int packed_rows(const sdrm_fsk_demod_batch *b, size_t in_stride, size_t input_len) {
+    return (in_stride & 1) == 0 && in_stride <= b->in_stride_dev && in_stride >= input_len &&
+           in_stride - input_len <= input_len / 16;
+}
+
 int sdrm_fsk_demod_batch_submit(sdrm_fsk_demod_batch *b, const float complex *input, size_t in_stride, size_t input_len) {
     if (b == NULL || (input == NULL && input_len > 0) || check_len(b, input_len) != 0) {
         return -1;
@@ -473,13 +489,62 @@ int sdrm_fsk_demod_batch_submit(sdrm_fsk_demod_batch *b, const float complex *in
     const int slot = (int) (b->submitted % SLOTS);
     code = ensure_staging(b, slot);
     if (code != 0) return code;
+    size_t dev_stride = b->in_stride_dev;
     if (input_len > 0) {
         /* staging buffer of call k - SLOTS was last read by its filters */
         if (b->submitted >= SLOTS) {
             SDRM_CUDA_TRY(cudaStreamWaitEvent(b->s_copy, b->ev_fir[slot], 0));
         }
-        SDRM_CUDA_TRY(cudaMemcpy2DAsync(b->d_in[slot], b->in_stride_dev * 8, input, in_stride * 8, input_len * 8, b->n_ch,
-                                        cudaMemcpyHostToDevice, b->s_copy));
+        if (packed_rows(b, in_stride, input_len)) {
+            /* rows (nearly) back to back: one linear copy keeps the host layout and runs at full PCIe rate (55.6 GB/s
+             * against 49.9 GB/s for the pitched copy, tools/microbench/h2d_probe.py) */
+            SDRM_CUDA_TRY(cudaMemcpyAsync(b->d_in[slot], input, ((size_t) (b->n_ch - 1) * in_stride + input_len) * 8,
+                                          cudaMemcpyHostToDevice, b->s_copy));
+            dev_stride = in_stride;
+        } else {
+            SDRM_CUDA_TRY(cudaMemcpy2DAsync(b->d_in[slot], b->in_stride_dev * 8, input, in_stride * 8, input_len * 8, b->n_ch,
+                                            cudaMemcpyHostToDevice, b->s_copy));
+        }
+    }
+    SDRM_CUDA_TRY(cudaEventRecord(b->ev_copy[slot], b->s_copy));
+    return enqueue(b, b->d_in[slot], dev_stride, input_len, slot, 1);
+}
+
+/* int16 IQ from the SDR (reference src/sdr/plutosdr.c:129 converts on the host): half the PCIe bytes, converted on the device */
+int sdrm_fsk_demod_batch_submit_i16(sdrm_fsk_demod_batch *b, const int16_t *input, size_t in_stride, size_t input_len, float scalar) {
+    if (b == NULL || (input == NULL && input_len > 0) || check_len(b, input_len) != 0) {
+        return -1;
+    }
+    if (b->submitted - b->fetched >= SLOTS) {
+        SDRM_LOG_ERROR("too many calls in flight: fetch results first");
+        return -EBUSY;
+    }
+    int code = set_device(b);
+    if (code != 0) return code;
+    const int slot = (int) (b->submitted % SLOTS);
+    code = ensure_staging(b, slot);
+    if (code == 0 && b->d_in16[slot] == NULL) {
+        code = sdrm_dev_zalloc(&b->d_in16[slot], (size_t) b->n_ch * b->in_stride_dev * 4);
+    }
+    if (code != 0) return code;
+    if (input_len > 0) {
+        if (b->submitted >= SLOTS) {
+            SDRM_CUDA_TRY(cudaStreamWaitEvent(b->s_copy, b->ev_fir[slot], 0));
+        }
+        size_t stride16 = b->in_stride_dev;
+        if (packed_rows(b, in_stride, input_len)) {
+            SDRM_CUDA_TRY(cudaMemcpyAsync(b->d_in16[slot], input, ((size_t) (b->n_ch - 1) * in_stride + input_len) * 4,
+                                          cudaMemcpyHostToDevice, b->s_copy));
+            stride16 = in_stride;
+        } else {
+            SDRM_CUDA_TRY(cudaMemcpy2DAsync(b->d_in16[slot], b->in_stride_dev * 4, input, in_stride * 4, input_len * 4, b->n_ch,
+                                            cudaMemcpyHostToDevice, b->s_copy));
+        }
+        code = sdrm_launch_code(sdrm_cu_i16_to_cf32(b->d_in16[slot], stride16, b->d_in[slot], b->in_stride_dev, scalar,
+                                                    (int) input_len, (int) b->n_ch, b->s_copy),
+                                "int16 ingest");
+        if (code != 0) return code;
+        b->launches++;
     }
     SDRM_CUDA_TRY(cudaEventRecord(b->ev_copy[slot], b->s_copy));
     return enqueue(b, b->d_in[slot], b->in_stride_dev, input_len, slot, 1);
@@ -631,6 +696,7 @@ void sdrm_fsk_demod_batch_destroy(sdrm_fsk_demod_batch *b) {
     }
     for (int s = 0; s < SLOTS; s++) {
         cudaFree(b->d_in[s]);
+        cudaFree(b->d_in16[s]);
         cudaFree(b->d_hard[s]);
         cudaFree(b->d_soft[s]);
         cudaFree(b->d_out_len[s]);
@@ -669,4 +735,24 @@ const char *sdrm_version(void) {
     cudaRuntimeGetVersion(&runtime);
     snprintf(text, sizeof(text), "sdr-modem_b200 0.1.0; sm_100a; CUDA runtime %d", runtime);
     return text;
+}
+
+/* ---- SDR sample formats on device buffers (include/sdrm/sdrm_batch.h) --------------------------------------------------- */
+
+int sdrm_samples_i16_to_cf32_device(const void *d_input, size_t in_stride, void *d_output, size_t out_stride, float scalar,
+                                    size_t len, uint32_t rows, void *stream) {
+    if (d_input == NULL || d_output == NULL || len > 0x7fffffffu) {
+        return -1;
+    }
+    return sdrm_launch_code(sdrm_cu_i16_to_cf32(d_input, in_stride, d_output, out_stride, scalar, (int) len, (int) rows, stream),
+                            "int16 -> cf32");
+}
+
+int sdrm_samples_cf32_to_i16_device(const void *d_input, size_t in_stride, void *d_output, size_t out_stride, float scalar,
+                                    size_t len, uint32_t rows, void *stream) {
+    if (d_input == NULL || d_output == NULL || len > 0x7fffffffu) {
+        return -1;
+    }
+    return sdrm_launch_code(sdrm_cu_cf32_to_i16(d_input, in_stride, d_output, out_stride, scalar, (int) len, (int) rows, stream),
+                            "cf32 -> int16");
 }

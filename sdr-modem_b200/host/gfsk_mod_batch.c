@@ -75,6 +75,7 @@ struct sdrm_gfsk_mod_batch_t {
     void *d_in;
     size_t in_stride_dev;
     void *d_out;
+    void *d_out16; /* int16 pairs, process_i16 only */
     size_t out_stride_dev;
     cudaStream_t stream;
     uint64_t launches;
@@ -212,6 +213,48 @@ int sdrm_gfsk_mod_batch_process(sdrm_gfsk_mod_batch *b, const uint8_t *input, si
     return 0;
 }
 
+/* as process, with the egress conversion of the PlutoSDR plugin (reference src/sdr/plutosdr.c:83) done on the device:
+ * output int16 (I, Q) pairs [channels][out_stride pairs] */
+int sdrm_gfsk_mod_batch_process_i16(sdrm_gfsk_mod_batch *b, const uint8_t *input, size_t in_stride, size_t input_len,
+                                    int16_t *output, size_t out_stride, float scalar, size_t *output_len) {
+    if (b == NULL || output == NULL || (input == NULL && input_len > 0) || mod_check(b, input_len) != 0) {
+        return -1;
+    }
+    SDRM_CUDA_TRY(cudaSetDevice(b->device));
+    const size_t n_out = input_len * 8 * (size_t) b->interpolation;
+    if (b->d_in == NULL) {
+        b->in_stride_dev = sdrm_round_up((size_t) b->max_bytes, 16) + 16;
+        int code = sdrm_dev_zalloc(&b->d_in, (size_t) b->n_ch * b->in_stride_dev);
+        if (code != 0) return code;
+        b->out_stride_dev = sdrm_round_up((size_t) b->max_bytes * 8 * (size_t) b->interpolation, 2) + 2;
+        code = sdrm_dev_zalloc(&b->d_out, (size_t) b->n_ch * b->out_stride_dev * 8);
+        if (code != 0) return code;
+    }
+    if (b->d_out16 == NULL) {
+        int code = sdrm_dev_zalloc(&b->d_out16, (size_t) b->n_ch * b->out_stride_dev * 4);
+        if (code != 0) return code;
+    }
+    if (input_len > 0) {
+        SDRM_CUDA_TRY(cudaMemcpy2DAsync(b->d_in, b->in_stride_dev, input, in_stride, input_len, b->n_ch, cudaMemcpyHostToDevice, b->stream));
+    }
+    int code = mod_enqueue(b, b->d_in, b->in_stride_dev, input_len, b->d_out, b->out_stride_dev);
+    if (code != 0) return code;
+    if (n_out > 0) {
+        code = sdrm_launch_code(sdrm_cu_cf32_to_i16(b->d_out, b->out_stride_dev, b->d_out16, b->out_stride_dev, scalar, (int) n_out,
+                                                    (int) b->n_ch, b->stream),
+                                "int16 egress");
+        if (code != 0) return code;
+        b->launches++;
+        SDRM_CUDA_TRY(cudaMemcpy2DAsync(output, out_stride * 4, b->d_out16, b->out_stride_dev * 4, n_out * 4, b->n_ch, cudaMemcpyDeviceToHost,
+                                        b->stream));
+    }
+    SDRM_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (output_len != NULL) {
+        *output_len = n_out;
+    }
+    return 0;
+}
+
 int sdrm_gfsk_mod_batch_sync(sdrm_gfsk_mod_batch *b) {
     if (b == NULL) {
         return -1;
@@ -240,6 +283,7 @@ void sdrm_gfsk_mod_batch_destroy(sdrm_gfsk_mod_batch *b) {
     cudaFree(b->d_work);
     cudaFree(b->d_in);
     cudaFree(b->d_out);
+    cudaFree(b->d_out16);
     free(b);
 }
 

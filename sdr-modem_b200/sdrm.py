@@ -44,7 +44,10 @@ def _load():
     lib.sdrm_fsk_demod_batch_create.argtypes = [C.POINTER(FskDemodBatchConfig), C.POINTER(vp)]
     lib.sdrm_fsk_demod_batch_process.argtypes = [vp, vp, sz, sz, vp, vp, sz, vp]
     lib.sdrm_fsk_demod_batch_submit.argtypes = [vp, vp, sz, sz]
+    lib.sdrm_fsk_demod_batch_submit_i16.argtypes = [vp, vp, sz, sz, C.c_float]
     lib.sdrm_fsk_demod_batch_process_device.argtypes = [vp, vp, sz, sz]
+    lib.sdrm_samples_i16_to_cf32_device.argtypes = [vp, sz, vp, sz, C.c_float, sz, C.c_uint32, vp]
+    lib.sdrm_samples_cf32_to_i16_device.argtypes = [vp, sz, vp, sz, C.c_float, sz, C.c_uint32, vp]
     lib.sdrm_fsk_demod_batch_fetch.argtypes = [vp, vp, vp, sz, vp]
     lib.sdrm_fsk_demod_batch_release.argtypes = [vp]
     lib.sdrm_fsk_demod_batch_device_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
@@ -71,6 +74,7 @@ def _load():
     lib.sdrm_gfsk_mod_batch_create.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32, i32, C.POINTER(vp)]
     lib.sdrm_gfsk_mod_batch_process.argtypes = [vp, vp, sz, sz, vp, sz, C.POINTER(sz)]
     lib.sdrm_gfsk_mod_batch_process_device.argtypes = [vp, vp, sz, sz, vp, sz]
+    lib.sdrm_gfsk_mod_batch_process_i16.argtypes = [vp, vp, sz, sz, vp, sz, C.c_float, C.POINTER(sz)]
     lib.sdrm_gfsk_mod_batch_sync.argtypes = [vp]
     lib.sdrm_gfsk_mod_batch_stream.restype = vp
     lib.sdrm_gfsk_mod_batch_stream.argtypes = [vp]
@@ -166,6 +170,18 @@ class FskDemodBatch:
 
     def submit_ptr(self, host_ptr, in_stride, n):
         _check(lib.sdrm_fsk_demod_batch_submit(self.handle, host_ptr, in_stride, n), "sdrm_fsk_demod_batch_submit")
+
+    def submit_i16(self, iq16, scalar=2048.0):
+        """iq16: int16 [channels, n, 2] (I, Q) as the SDR delivers it; converted on the device (plutosdr.c:129)."""
+        iq16 = np.ascontiguousarray(iq16, dtype=np.int16)
+        assert iq16.ndim == 3 and iq16.shape[0] == self.n_channels and iq16.shape[2] == 2
+        self._keep = iq16
+        _check(lib.sdrm_fsk_demod_batch_submit_i16(self.handle, iq16.ctypes.data_as(C.c_void_p), iq16.shape[1], iq16.shape[1],
+                                                   scalar), "sdrm_fsk_demod_batch_submit_i16")
+
+    def submit_i16_ptr(self, host_ptr, in_stride, n, scalar=2048.0):
+        _check(lib.sdrm_fsk_demod_batch_submit_i16(self.handle, host_ptr, in_stride, n, scalar),
+               "sdrm_fsk_demod_batch_submit_i16")
 
     def fetch(self, hard=None, lens=None, soft=None):
         cap = self.capacity
@@ -409,6 +425,18 @@ class GfskModBatch:
         _check(lib.sdrm_gfsk_mod_batch_process(self.handle, data.ctypes.data_as(C.c_void_p), data.shape[1], data.shape[1],
                                                out.ctypes.data_as(C.c_void_p), out.shape[1], C.byref(produced)),
                "sdrm_gfsk_mod_batch_process")
+        return out[:, :produced.value]
+
+    def process_i16(self, data, scalar=32768.0):
+        """bytes in, int16 (I, Q) pairs out [channels, n, 2]: the PlutoSDR egress format (plutosdr.c:83)"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert data.ndim == 2 and data.shape[0] == self.n_channels
+        n_out = data.shape[1] * 8 * self.interpolation
+        out = np.zeros((self.n_channels, max(n_out, 1), 2), dtype=np.int16)
+        produced = C.c_size_t()
+        _check(lib.sdrm_gfsk_mod_batch_process_i16(self.handle, data.ctypes.data_as(C.c_void_p), data.shape[1], data.shape[1],
+                                                   out.ctypes.data_as(C.c_void_p), out.shape[1], scalar, C.byref(produced)),
+               "sdrm_gfsk_mod_batch_process_i16")
         return out[:, :produced.value]
 
     def process_device(self, d_in, in_stride, n_bytes, d_out, out_stride):
