@@ -316,3 +316,36 @@ double ref_bench_gfsk_mod(float sps, float sensitivity, float bt, const uint8_t 
     if (samples_out != NULL) *samples_out = samples;
     return failed ? -1.0 : elapsed;
 }
+
+/*
+ * Orbit model known answers: the reference's own SGP4 / SDP4 (src/sgpsdp) evaluated at a sequence of times on ONE
+ * satellite object (the deep-space resonance integrator carries state between calls), as doppler_calculate_shift
+ * does (reference src/dsp/doppler.c:31-42). out: n x 6 doubles (position km, velocity km/s). Returns 1 for a
+ * deep-space element set, 0 for near-earth, -1 for an invalid element set.
+ */
+#include "sgpsdp/sgp4sdp4.h"
+
+int ref_orbit_states(char tle[3][80], const double *tsince, size_t n, double *out) {
+    sat_t sat;
+    memset(&sat, 0, sizeof(sat));
+    if (Get_Next_Tle_Set(tle, &sat.tle) != 1) {
+        return -1;
+    }
+    select_ephemeris(&sat);
+    const int deep = (sat.flags & DEEP_SPACE_EPHEM_FLAG) != 0;
+    for (size_t i = 0; i < n; i++) {
+        if (deep) {
+            SDP4(&sat, tsince[i]);
+        } else {
+            SGP4(&sat, tsince[i]);
+        }
+        Convert_Sat_State(&sat.pos, &sat.vel);
+        out[6 * i + 0] = sat.pos.x;
+        out[6 * i + 1] = sat.pos.y;
+        out[6 * i + 2] = sat.pos.z;
+        out[6 * i + 3] = sat.vel.x;
+        out[6 * i + 4] = sat.vel.y;
+        out[6 * i + 5] = sat.vel.z;
+    }
+    return deep;
+}

@@ -97,11 +97,7 @@ int sdrm_doppler_batch_create(uint32_t n_channels, const sdrm_doppler_channel *c
         }
         const int code = sdrm_orbit_init(channels[i].tle, &c->orbit);
         if (code != 0) {
-            if (code == -2) {
-                SDRM_LOG_ERROR("deep-space orbits (SDP4) are not supported by the Doppler schedule yet");
-            } else {
-                SDRM_LOG_ERROR("invalid tle configuration");
-            }
+            SDRM_LOG_ERROR("invalid tle configuration");
             sdrm_doppler_batch_destroy(b);
             return -1;
         }

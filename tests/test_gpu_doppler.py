@@ -102,3 +102,22 @@ def test_doppler_batch_channels_with_their_own_clocks(sdrm, ref):
     for c in range(n_ch):
         want = ref.doppler(LAT, LON, 0.0, fs, 437525000, 100 * c, starts[c], 4096, LUCKY7_TLE).run(x[c], 4096)
         assert close_trig(got[c], want)
+
+
+# Spacetrack Report #3 SDP4 test case (reference test/resources/test-002.tle): period 10.5 h, e = 0.73, 12 h resonance
+MOLNIYA_LIKE_TLE = ["TEST SAT SDP 001",
+                    "1 11801U          80230.29629788  .01431103  00000-0  14311-1 0     2",
+                    "2 11801  46.7916 230.4354 7318036  47.4722  10.4117  2.28537848     2"]
+
+
+def test_doppler_deep_space_satellite(sdrm, ref):
+    """a deep-space element set goes through SDP4 (reference src/dsp/doppler.c:33-34): 120 one-second schedule updates"""
+    fs, n = 2000, 240000
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    start = 335000000 + 86400 * 3  # a few days after the element set's epoch (1980 day 230)
+    want = ref.doppler(LAT, LON, 0.0, fs, 145900000, 0, start, 3000, MOLNIYA_LIKE_TLE).run(x, 2500)
+    d = DopplerHandle(sdrm.lib, LAT, LON, 0.0, fs, 145900000, 0, start, 3000, MOLNIYA_LIKE_TLE)
+    got = d.run(x, 2500)
+    d.close()
+    assert close_trig(got, want)

@@ -217,3 +217,15 @@ def test_port_equals_ref_nco_and_mod(port, ref):
         pm, rm = port.GfskMod(sps, sens, 0.5, 200), ref.gfsk_mod(sps, sens, 0.5, 200)
         for part in (data[:200], data[200:]):
             assert same_bits(pm.process(part), rm.process(part))
+
+
+def test_sample_format_converts_match_reference_kats(port):
+    """orc_convert_16i_32f / orc_convert_32f_16i against the reference's PlutoSDR known answers (test/test_plutosdr.c:149-154,
+    192-194): rx int16 i -> i / 2048 printed to 6 decimals, tx x * 32768 -> 0, 16, 32 ..."""
+    rx = port.convert_16i_32f(np.arange(50, dtype=np.int16), 2048.0)
+    assert np.array_equal(rx, (np.arange(50) / 2048.0).astype(np.float32))
+    printed = np.array([float("%.6f" % v) for v in rx], dtype=np.float32)
+    tx = port.convert_32f_16i(printed, 32768.0)
+    assert np.array_equal(tx, np.arange(50, dtype=np.int16) * 16)
+    edge = np.array([1.0, -1.0, 2.0, -2.0, 0.5 / 32768, 1.5 / 32768, 2.5 / 32768, -0.5 / 32768, np.nan], dtype=np.float32)
+    assert list(port.convert_32f_16i(edge, 32768.0)) == [32767, -32768, 32767, -32768, 0, 2, 2, 0, 0]

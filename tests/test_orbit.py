@@ -1,0 +1,118 @@
+"""CPU: the host orbit model (sdr-modem_b200/host/orbit.c: TLE parsing, SGP4, SDP4) against the reference's known answers
+(test/test_sgp4_001.c, test/test_sgp4_002.c) and against the reference's own src/sgpsdp (oracle/_ref) on element sets that
+reach every deep-space branch, with time sequences that drive the resonance integrator forwards, backwards and across the
+epoch."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+FIXTURES = json.load(open(os.path.join(ROOT, "tests", "golden", "tle_fixtures.json")))
+
+
+def checksum(line):
+    return sum(int(c) if c.isdigit() else (1 if c == "-" else 0) for c in line[:68]) % 10
+
+
+def make_tle(incl, raan, ecc, argp, ma, mm, epoch="20069.88080907", bstar=" 32890-4"):
+    l1 = "1 99999U 20001A   %s  .00000505  00000-0 %s 0  999" % (epoch, bstar)
+    l2 = "2 99999 %8.4f %8.4f %07d %8.4f %8.4f %11.8f    1" % (incl, raan, int(round(ecc * 1e7)), argp, ma, mm)
+    assert len(l1) == 68 and len(l2) == 68
+    return ["SYNTHETIC", l1 + str(checksum(l1)), l2 + str(checksum(l2))]
+
+
+def tle_buffer(lines):
+    buf = ((C.c_char * 80) * 3)()
+    for i, line in enumerate(lines):
+        raw = line.encode("ascii")
+        C.memmove(C.addressof(buf[i]), raw + b"\0", len(raw) + 1)
+    return buf
+
+
+class Orbit:
+    def __init__(self, lib, lines):
+        self.lib = lib
+        self.mem = C.create_string_buffer(8192)  # sdrm_orbit is an internal struct of < 2 KB
+        lib.sdrm_orbit_init.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sdrm_orbit_state.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        lib.sdrm_orbit_state.restype = None
+        self.code = lib.sdrm_orbit_init(tle_buffer(lines), self.mem)
+
+    def states(self, times):
+        out = np.zeros((len(times), 6))
+        for i, t in enumerate(times):
+            pos, vel = (C.c_double * 3)(), (C.c_double * 3)()
+            self.lib.sdrm_orbit_state(self.mem, float(t), pos, vel)
+            out[i, :3], out[i, 3:] = list(pos), list(vel)
+        return out
+
+
+def reference_states(lines, times):
+    from oracle import ref
+    lib = ref.load()
+    lib.ref_orbit_states.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    t = np.ascontiguousarray(times, dtype=np.float64)
+    out = np.zeros((len(t), 6))
+    deep = lib.ref_orbit_states(tle_buffer(lines), t.ctypes.data_as(C.c_void_p), len(t), out.ctypes.data_as(C.c_void_p))
+    return deep, out
+
+
+@pytest.mark.parametrize("name", ["test-001", "test-002"])
+def test_reference_known_answers(sdrm, name):
+    """reference test/test_sgp4_001.c (SGP4) and test/test_sgp4_002.c (SDP4): 1e-5 km and km/s, as the reference asserts"""
+    fx = FIXTURES[name]
+    orbit = Orbit(sdrm.lib, fx["tle"])
+    assert orbit.code == 0
+    expected = np.array(fx["expected"])
+    got = orbit.states(expected[:, 0])
+    assert np.abs(got - expected[:, 1:]).max() < 1e-5
+
+
+SEQUENCE = [0, 10, 360, 725, 1500, 5000, 20000, 19000, 4000, 100, -50, -800, -3000, -100, 30, 2880, 2885, 2900, 100000]
+
+DEEP_CASES = {
+    "molniya 12 h resonance, e > 0.715": (63.4, 120.0, 0.7318036, 270.0, 10.0, 2.00600000),
+    "12 h resonance, 0.65 < e <= 0.715": (63.4, 40.0, 0.7000000, 280.0, 300.0, 2.00570000),
+    "12 h resonance, e <= 0.65": (55.0, 300.0, 0.6000000, 90.0, 45.0, 1.95000000),
+    "24 h synchronous": (0.0500, 80.0, 0.0003000, 150.0, 220.0, 1.00270000),
+    "24 h synchronous inclined": (14.0, 10.0, 0.0100000, 30.0, 330.0, 1.00100000),
+    "gps-like, not resonant (e < 0.5)": (55.0, 150.0, 0.0100000, 200.0, 100.0, 2.00560000),
+    "low inclination (Lyddane), not resonant": (7.0, 200.0, 0.3000000, 20.0, 10.0, 3.50000000),
+    "high eccentric deep, 4 rev/day": (28.5, 10.0, 0.5500000, 180.0, 0.0, 4.20000000),
+    "inclination below 3 degrees (no node rate)": (2.0, 333.0, 0.2000000, 45.0, 90.0, 1.50000000),
+}
+
+
+@pytest.mark.parametrize("case", list(DEEP_CASES))
+def test_sdp4_matches_reference_sources(sdrm, case):
+    lines = make_tle(*DEEP_CASES[case])
+    deep, want = reference_states(lines, SEQUENCE)
+    assert deep == 1
+    orbit = Orbit(sdrm.lib, lines)
+    assert orbit.code == 0
+    got = orbit.states(SEQUENCE)
+    scale = np.maximum(np.abs(want), 1.0)
+    assert (np.abs(got - want) / scale).max() < 1e-9, case
+
+
+@pytest.mark.parametrize("mm,ecc", [(15.12089395, 0.0026284), (16.05824518, 0.0086731), (12.5, 0.1), (6.5, 0.02), (7.0, 0.4)])
+def test_sgp4_matches_reference_sources(sdrm, mm, ecc):
+    lines = make_tle(97.527, 32.5584, ecc, 107.4758, 252.9348, mm)
+    deep, want = reference_states(lines, SEQUENCE)
+    assert deep == 0
+    got = Orbit(sdrm.lib, lines).states(SEQUENCE)
+    scale = np.maximum(np.abs(want), 1.0)
+    assert (np.abs(got - want) / scale).max() < 1e-12
+
+
+def test_invalid_element_sets(sdrm):
+    good = FIXTURES["test-002"]["tle"]
+    assert Orbit(sdrm.lib, good).code == 0
+    bad_checksum = [good[0], good[1][:-1] + "5", good[2]]
+    assert Orbit(sdrm.lib, bad_checksum).code == -1
+    wrong_number = [good[0], good[1], "2 11802" + good[2][7:]]
+    assert Orbit(sdrm.lib, wrong_number).code == -1
