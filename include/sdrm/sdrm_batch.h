@@ -184,6 +184,28 @@ uint64_t sdrm_gfsk_mod_batch_launch_count(const sdrm_gfsk_mod_batch *batch);
 void sdrm_gfsk_mod_batch_destroy(sdrm_gfsk_mod_batch *batch);
 
 /*
+ * N x lpf (reference src/dsp/lpf.c:12-51): one low-pass filter design, N streams with their own history, complex
+ * (num_bytes 8) or real (num_bytes 4) samples, decimation as in lpf_create. All streams receive the same number of samples
+ * per call, so they all produce the same number of outputs (*output_len).
+ * Strides are in samples of the stream's type.
+ */
+typedef struct sdrm_lpf_batch_t sdrm_lpf_batch;
+
+int sdrm_lpf_batch_create(uint32_t n_channels, uint8_t decimation, uint64_t sampling_freq, uint64_t cutoff_freq,
+                          uint32_t transition_width, uint32_t max_input_buffer_length, size_t num_bytes, int device,
+                          sdrm_lpf_batch **batch);
+/* host buffers [channels][stride] */
+int sdrm_lpf_batch_process(sdrm_lpf_batch *batch, const void *input, size_t in_stride, size_t input_len, void *output,
+                           size_t out_stride, size_t *output_len);
+/* device buffers, asynchronous on the batch's stream; complex rows 16-byte aligned with an even stride */
+int sdrm_lpf_batch_process_device(sdrm_lpf_batch *batch, const void *d_input, size_t in_stride, size_t input_len,
+                                  void *d_output, size_t out_stride, size_t *output_len);
+int sdrm_lpf_batch_sync(sdrm_lpf_batch *batch);
+void *sdrm_lpf_batch_stream(sdrm_lpf_batch *batch);
+uint64_t sdrm_lpf_batch_launch_count(const sdrm_lpf_batch *batch);
+void sdrm_lpf_batch_destroy(sdrm_lpf_batch *batch);
+
+/*
  * SDR sample formats on device buffers (reference src/sdr/plutosdr.c:83,129; VOLK generic 16i <-> 32f kernels), rows of
  * `len` complex samples, strides in complex samples, asynchronous on `stream` (a cudaStream_t, NULL = default stream).
  */

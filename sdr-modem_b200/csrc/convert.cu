@@ -80,3 +80,56 @@ extern "C" int sdrm_cu_cf32_to_i16(const void *in, size_t in_stride, void *out, 
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }
+
+// Real streams ride through the FIR two channels at a time (PAIR layout, sdrm_cuda.h): these two passes move between
+// channel rows float [ch][stride] and pair rows float2 [ch / 2][stride] = (ch 2p, ch 2p + 1). An odd last channel is
+// paired with zeros.
+namespace {
+
+__global__ void rows_to_pairs_kernel(const float *__restrict__ in, size_t in_stride, float2 *__restrict__ out, size_t out_stride,
+                                     int n, int n_ch) {
+    const int p = blockIdx.y;
+    const float *a = in + (size_t) (2 * p) * in_stride;
+    const float *b = 2 * p + 1 < n_ch ? in + (size_t) (2 * p + 1) * in_stride : nullptr;
+    float2 *y = out + (size_t) p * out_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        y[i] = make_float2(a[i], b != nullptr ? b[i] : 0.0f);
+    }
+}
+
+__global__ void pairs_to_rows_kernel(const float2 *__restrict__ in, size_t in_stride, float *__restrict__ out, size_t out_stride,
+                                     int n, int n_ch) {
+    const int p = blockIdx.y;
+    const float2 *x = in + (size_t) p * in_stride;
+    float *a = out + (size_t) (2 * p) * out_stride;
+    float *b = 2 * p + 1 < n_ch ? out + (size_t) (2 * p + 1) * out_stride : nullptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 v = x[i];
+        a[i] = v.x;
+        if (b != nullptr) {
+            b[i] = v.y;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int sdrm_cu_rows_to_pairs(const float *in, size_t in_stride, void *out, size_t out_stride, int n, int n_ch, void *stream) {
+    if (n <= 0 || n_ch <= 0) {
+        return 0;
+    }
+    rows_to_pairs_kernel<<<convert_grid(n, (n_ch + 1) / 2), 256, 0, (cudaStream_t) stream>>>(in, in_stride, (float2 *) out, out_stride,
+                                                                                            n, n_ch);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}
+
+extern "C" int sdrm_cu_pairs_to_rows(const void *in, size_t in_stride, float *out, size_t out_stride, int n, int n_ch, void *stream) {
+    if (n <= 0 || n_ch <= 0) {
+        return 0;
+    }
+    pairs_to_rows_kernel<<<convert_grid(n, (n_ch + 1) / 2), 256, 0, (cudaStream_t) stream>>>((const float2 *) in, in_stride, out,
+                                                                                            out_stride, n, n_ch);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}

@@ -226,6 +226,10 @@ int sdrm_cu_i16_to_cf32(const void *in, size_t in_stride, void *out, size_t out_
 int sdrm_cu_cf32_to_i16(const void *in, size_t in_stride, void *out, size_t out_stride, float scalar, int n, int rows,
                         void *stream);
 
+/* channel rows float [n_ch][stride] <-> PAIR rows float2 [(n_ch + 1) / 2][stride]; an odd last channel pairs with zeros */
+int sdrm_cu_rows_to_pairs(const float *in, size_t in_stride, void *out, size_t out_stride, int n, int n_ch, void *stream);
+int sdrm_cu_pairs_to_rows(const void *in, size_t in_stride, float *out, size_t out_stride, int n, int n_ch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,17 @@ def _load():
     lib.sdrm_gfsk_mod_batch_launch_count.argtypes = [vp]
     lib.sdrm_gfsk_mod_batch_destroy.argtypes = [vp]
     lib.sdrm_gfsk_mod_batch_destroy.restype = None
+    lib.sdrm_lpf_batch_create.argtypes = [C.c_uint32, C.c_uint8, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, sz, i32,
+                                          C.POINTER(vp)]
+    lib.sdrm_lpf_batch_process.argtypes = [vp, vp, sz, sz, vp, sz, C.POINTER(sz)]
+    lib.sdrm_lpf_batch_process_device.argtypes = [vp, vp, sz, sz, vp, sz, C.POINTER(sz)]
+    lib.sdrm_lpf_batch_sync.argtypes = [vp]
+    lib.sdrm_lpf_batch_stream.restype = vp
+    lib.sdrm_lpf_batch_stream.argtypes = [vp]
+    lib.sdrm_lpf_batch_launch_count.restype = C.c_uint64
+    lib.sdrm_lpf_batch_launch_count.argtypes = [vp]
+    lib.sdrm_lpf_batch_destroy.argtypes = [vp]
+    lib.sdrm_lpf_batch_destroy.restype = None
     lib.sdrm_doppler_batch_create.argtypes = [C.c_uint32, vp, C.c_uint64, C.c_uint64, C.c_uint32, i32, C.POINTER(vp)]
     lib.sdrm_doppler_batch_process.argtypes = [vp, i32, vp, sz, sz, vp, sz]
     lib.sdrm_doppler_batch_process_device.argtypes = [vp, i32, vp, sz, sz, vp, sz]
@@ -397,6 +408,52 @@ class NcoBatch:
     def close(self):
         if self.handle:
             lib.sdrm_nco_batch_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LpfBatch:
+    """N x lpf (reference src/dsp/lpf.c): one design, N streams, complex or real samples."""
+
+    def __init__(self, n_channels, decimation, sampling_freq, cutoff_freq, transition_width, max_len, complex_samples=True,
+                 device=-1):
+        self.handle = C.c_void_p()
+        self.n_channels = n_channels
+        self.dtype = np.complex64 if complex_samples else np.float32
+        _check(lib.sdrm_lpf_batch_create(n_channels, decimation, sampling_freq, cutoff_freq, transition_width, max_len,
+                                         8 if complex_samples else 4, device, C.byref(self.handle)), "sdrm_lpf_batch_create")
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        assert x.ndim == 2 and x.shape[0] == self.n_channels
+        out = np.zeros((self.n_channels, max(x.shape[1], 1)), dtype=self.dtype)
+        produced = C.c_size_t()
+        _check(lib.sdrm_lpf_batch_process(self.handle, x.ctypes.data_as(C.c_void_p), x.shape[1], x.shape[1],
+                                          out.ctypes.data_as(C.c_void_p), out.shape[1], C.byref(produced)),
+               "sdrm_lpf_batch_process")
+        return out[:, :produced.value]
+
+    def process_device(self, d_in, in_stride, n, d_out, out_stride):
+        produced = C.c_size_t()
+        _check(lib.sdrm_lpf_batch_process_device(self.handle, C.c_void_p(d_in), in_stride, n, C.c_void_p(d_out), out_stride,
+                                                 C.byref(produced)), "sdrm_lpf_batch_process_device")
+        return produced.value
+
+    def sync(self):
+        _check(lib.sdrm_lpf_batch_sync(self.handle), "sdrm_lpf_batch_sync")
+
+    @property
+    def stream(self):
+        return lib.sdrm_lpf_batch_stream(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib.sdrm_lpf_batch_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):

@@ -148,6 +148,23 @@ def test_fir_filter_float_single(sdrm):
     f.close()
 
 
+@pytest.mark.parametrize("n_ch,dec,cplx,chunk", [(5, 1, True, 777), (8, 2, True, 1000), (3, 5, True, 4096), (7, 2, False, 999),
+                                                 (4, 3, False, 4096), (1, 1, False, 50)])
+def test_lpf_batch_bit_exact(sdrm, port, n_ch, dec, cplx, chunk):
+    """sdrm_lpf_batch: N streams through one filter design, each equal to its own lpf handle of the reference"""
+    x = np.stack([noise(9000, 100 + c, cplx) for c in range(n_ch)])
+    b = sdrm.LpfBatch(n_ch, dec, 48000, 4800, 2000, 4096, cplx)
+    parts = [b.process(x[:, o:o + chunk]) for o in range(0, x.shape[1], chunk)]
+    assert b.process(x[:, :0]).shape[1] == 0
+    with pytest.raises(sdrm.SdrmError):
+        b.process(x[:, :5000])
+    b.close()
+    y = np.concatenate(parts, axis=1)
+    taps = port.low_pass_taps(1.0, 48000, 4800, 2000)
+    for c in range(n_ch):
+        assert same_bits(y[c], port.Fir(taps, dec, cplx).run(x[c], chunk))
+
+
 def test_quadrature_demod(sdrm, port, kats):
     q = make_quad(sdrm.lib, 25.4, 2000)
     x = complex_ramp(200)
