@@ -249,3 +249,37 @@ def test_rx_group_socket_and_failures(sdrm, port):
     cfg = group_config(4096)
     cfg.queue_size = 0
     assert lib.sdrm_rx_group_create(C.byref(cfg), sessions, 1, C.byref(g)) == -1
+
+
+def test_handles_are_reentrant_across_threads(sdrm, port):
+    """SURVEY §8b threading: one handle per thread, different handles concurrently (the reference runs one dsp thread per RX
+    session and one tcp thread per TX session). 6 threads, each with its own fsk_demod and gfsk_mod handle, all at once."""
+    import threading
+    _, _, args = FSK_GOLDENS["lucky7"]
+    iq = golden_array("lucky7.expected.cf32", np.complex64)
+    want, _ = port.FskDemod(*args, 4096).run(iq, 4096)
+    sens = float(np.float32(2 * np.pi * 5000 / 19200))
+    data = np.random.default_rng(4).integers(0, 256, 777, dtype=np.uint8)
+    want_mod = port.GfskMod(2.0, sens, 0.5, 1024).process(data)
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            d = sdrm.FskDemod(*args, 4096)
+            parts = [d.process(iq[o:o + 4096]) for o in range(0, len(iq), 4096)]
+            m = sdrm.GfskModBatch(1, 2.0, sens, 0.5, 1024)
+            results[i] = (np.concatenate(parts), m.process(data[None, :])[0])
+            m.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    for i in range(6):
+        assert same_bits(results[i][0], want)
+        # double cos/sin rounded to float: CUDA and glibc may differ in the last place about once in 1e8 samples
+        assert len(results[i][1]) == len(want_mod) and np.mean(results[i][1] == want_mod) > 0.9999

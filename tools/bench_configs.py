@@ -2,6 +2,8 @@
 """Secondary benchmark lines (not the driver's contract; that is bench.py = BASELINE configs[1]):
 
   python tools/bench_configs.py --config c4 [--channels 1024]   gfsk_mod batch, 2048-byte packets, sps 2 (configs[3])
+  python tools/bench_configs.py --config c1                      one channel on one host core, reference CPU chain (configs[0])
+  python tools/bench_configs.py --config c3alt                   configs[2] recomposed as doppler -> decimating lpf -> fsk_demod
   python tools/bench_configs.py --config c3 [--channels 4096]   doppler + GMSK 2400 baud from 2.4 Msps, decim 100 (configs[2])
 
 Each prints one JSON line with the device-resident throughput, the roofline that bounds the stage, and the reference's
@@ -158,9 +160,92 @@ def bench_c3(args):
         "cpu_baseline": cpu, "error_flags": demod.error_flags()}))
 
 
+def bench_c1(args):
+    """BASELINE configs[0]: ONE channel on ONE host core through the reference's own CPU chain (oracle/_ref), 10 s of signal in
+    4096-sample calls; plus the reference's published perf shape (test/perf_fsk_modem.c: 48 kHz, 4800 baud, input (uint8) i)."""
+    from oracle import ref
+    import workloads
+    out = {}
+    for name, shape, n in (("c1_192k_9600", workloads.C2_PARITY, 1920000), ("perf_fsk_modem_48k_4800", workloads.PERF_SHAPE, 480000)):
+        if name.startswith("perf"):
+            iq = ((np.arange(n) % 256).astype(np.float32) + 0j).astype(np.complex64)[None, :]
+        else:
+            iq = workloads.gfsk_channels(1, n, shape, seed=1000, device="cpu").numpy()
+        sec, symbols = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, 1, passes=1)
+        out[name] = {"msamples_per_s": n / sec / 1e6, "seconds": sec, "samples": n, "symbols": int(symbols), "chunk": shape.chunk}
+    print(json.dumps({"metric": "demodulated Msamples/s", "value": out["c1_192k_9600"]["msamples_per_s"], "unit": "Msamples/s",
+                      "n_gpus": 0, "impl": "reference", "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "1 channel, 1 core, oracle/_ref strict build (BASELINE configs[0])"},
+                      "cpu_baseline": {"cores": 1, "kind": "reference"}, "shapes": out}))
+
+
+def bench_c3alt(args):
+    """The same sessions as C3 composed the other legal way: doppler -> complex decimating lpf (dec 25, 2.4 Msps ->
+    96 ksps) -> fsk_demod at the low rate (decim 4). Not the parity-defining chain; shows what the public API allows."""
+    import torch
+    import sdrm
+    import workloads
+    n_ch, chunk, dec1 = args.channels, 131072, 25
+    shape = workloads.DemodShape("gmsk2400@2.4M/chunk131072", 2400000, 2400, 5000, 100, 2000, True, chunk)
+    lat, lon = float(np.float32(53.72)), float(np.float32(47.57))
+    channels = [sdrm.doppler_channel(lat, lon, 0.0, 0, 1583840449 + c, LUCKY7_TLE) for c in range(n_ch)]
+    dop = sdrm.DopplerBatch(channels, shape.sampling_freq, 437525000, chunk, device=0)
+    lpf = sdrm.LpfBatch(n_ch, dec1, shape.sampling_freq, 20000, 10000, chunk, True, device=0)
+    low_len = chunk // dec1 + 1
+    demod = sdrm.FskDemodBatch(n_ch, shape.sampling_freq // dec1, 2400, 5000, 4, 2000, True, low_len,
+                               max_symbols_per_call=int(low_len / 40 * 1.2) + 64, device=0)
+    iq = workloads.gfsk_channels(n_ch, 2 * chunk, shape, seed=3000, device="cuda", max_offset_hz=4000.0)
+    bufs = [iq[:, i * chunk:(i + 1) * chunk].contiguous() for i in range(2)]
+    del iq
+    corrected = torch.empty((n_ch, chunk), dtype=torch.complex64, device="cuda")
+    low_stride = low_len + (low_len & 1)
+    low = [torch.empty((n_ch, low_stride), dtype=torch.complex64, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    dop_stream = torch.cuda.ExternalStream(dop.stream)
+    lpf_stream = torch.cuda.ExternalStream(lpf.stream)
+    fir_stream = torch.cuda.ExternalStream(demod.stream)
+    tail_stream = torch.cuda.ExternalStream(demod.tail_stream)
+    ev_dop, ev_lpf, ev_low_free = torch.cuda.Event(), torch.cuda.Event(), [torch.cuda.Event(), torch.cuda.Event()]
+
+    def step(k):
+        dop_stream.wait_stream(lpf_stream)  # `corrected` is reused every step
+        dop.process_device(bufs[k % 2].data_ptr(), chunk, chunk, corrected.data_ptr(), chunk, direction=1)
+        ev_dop.record(dop_stream)
+        lpf_stream.wait_event(ev_dop)
+        lpf_stream.wait_event(ev_low_free[k % 2])
+        n_low = lpf.process_device(corrected.data_ptr(), chunk, chunk, low[k % 2].data_ptr(), low_stride)
+        ev_lpf.record(lpf_stream)
+        fir_stream.wait_event(ev_lpf)
+        demod.process_device(low[k % 2].data_ptr(), low_stride, n_low)
+        ev_low_free[k % 2].record(fir_stream)
+        demod.release()
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(dop_stream)
+    for k in range(args.steps):
+        step(k)
+    end.record(tail_stream)
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / args.steps
+    value = n_ch * chunk / (ms * 1e-3) / 1e6
+    pk, kind = peaks()
+    print(json.dumps({
+        "metric": "demodulated Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d channels x doppler -> lpf(dec %d, cutoff 20 kHz, tw 10 kHz) -> fsk_demod(96 ksps, 2400 baud, "
+                               "decim 4, dc on): BASELINE configs[2] recomposed, NOT the parity-defining chain" % (n_ch, dec1)},
+        "roofline": {"bound": "hbm", "achieved": value * 1e6 * 24 / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": value * 1e6 * 24 / 1e9 / pk["hbm_gbs"],
+                     "note": "24 algorithmic B per input sample: doppler 8 in + 8 out, lpf 8 in (+ 8/25 out)"},
+        "error_flags": demod.error_flags()}))
+
+
 def main():
     p = argparse.ArgumentParser()
-    p.add_argument("--config", required=True, choices=["c3", "c4"])
+    p.add_argument("--config", required=True, choices=["c1", "c3", "c3alt", "c4"])
     p.add_argument("--channels", type=int, default=None)
     p.add_argument("--steps", type=int, default=None)
     p.add_argument("--warmup", type=int, default=3)
@@ -170,6 +255,12 @@ def main():
         args.channels = args.channels or 1024
         args.steps = args.steps or 50
         bench_c4(args)
+    elif args.config == "c1":
+        bench_c1(args)
+    elif args.config == "c3alt":
+        args.channels = args.channels or 1024
+        args.steps = args.steps or 10
+        bench_c3alt(args)
     else:
         args.channels = args.channels or 4096
         args.steps = args.steps or 3
