@@ -40,6 +40,8 @@ constexpr int kBlockRows = 32;             // rows per pipeline step
 constexpr int kTile = kBlockRows * 32;     // floats per [row][lane] tile (4 KB)
 constexpr int kRowBytes = 32 * 4;          // one row of 32 channels
 constexpr int kGuard = 16;                 // slack between what a lane may lag behind and the size of its ring
+constexpr int kMirror = 16;                // ring rows [0, kMirror) are kept twice, again at [slots, slots + kMirror), so
+                                           // that the clock's 11-sample window never wraps
 constexpr int kTapsFloats = 129 * 8 + 24;  // MMSE bank, padded to a multiple of 128 bytes
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -132,7 +134,9 @@ __device__ __forceinline__ float div_by_length(float sum, float length_f, float 
     const float q2 = __fmaf_rn(e1, rcp, q1);
     const float mag = fabsf(sum);
     redo |= !(mag < 1.0e18f) || (mag < 1.0e-18f && sum != 0.0f);
-    return sum == 0.0f ? sum : q2;  // keeps the sign of a zero sum
+    // a zero sum: +0 gives q0 = e0 = q1 = ... = +0. (-0 would come back as +0, but the running sums of this kernel are never
+    // -0: they start at +0 and RN(x + (-x)) = +0; the per-block dc_blocker handle in tail.cu keeps the explicit test.)
+    return q2;
 }
 
 // Shared-memory map of one CTA.
@@ -161,8 +165,31 @@ __device__ __forceinline__ float *group_dx(const sdrm_tail_args &a, int group) {
 // One elected lane fetches block b for this warp's stage: its rows of the TC ring (warp 0), the stage's own inputs of L
 // rows ago (its delay line) and, for the last stage, x[n - (2L - 2)] from the group delay line. Completion is counted on
 // the warp's mbarrier of parity b & 1.
+// Cursors of a producer warp into the circular arrays, for the block it is working on. They advance by one block per
+// step with a compare-and-subtract (all lengths are >= 32 rows); a 64-bit modulo per copy, as a first version had, was a
+// quarter of all instructions the kernel executed, on one lane, in front of everything else.
+struct Cursors {
+    int line;      // stage delay line: slot of the block's first row
+    int dx_store;  // group delay line: where the first stage writes
+    int dx_load;   // group delay line: where the last stage reads x[n - (2L - 2)]
+};
+
+__device__ __forceinline__ int advance(int pos, int len) {
+    pos += kBlockRows;
+    return pos >= len ? pos - len : pos;
+}
+
+__device__ __forceinline__ Cursors next_block(const sdrm_tail_args &a, const Cursors &c) {
+    Cursors n;
+    n.line = advance(c.line, a.dc_length);
+    n.dx_store = advance(c.dx_store, a.dx_length);
+    n.dx_load = advance(c.dx_load, a.dx_length);
+    return n;
+}
+
 template <int PROD>
-__device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layout &s, int warp, int lane, int group, int b) {
+__device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layout &s, int warp, int lane, int group, int b,
+                                            const Cursors &c) {
     if (lane != 0) {
         return;
     }
@@ -178,12 +205,18 @@ __device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layou
         bulk_load_rows(s.rows + parity * kTile, group_rows(a, group), first, nr, a.ring_rows, bar);
     }
     if (has_dc) {
-        const int slot = (int) (((long long) a.pos_l + row0) % a.dc_length);
-        bulk_load_rows(s.line + (warp * 2 + parity) * kTile, group_line(a, group, warp), slot, nr, a.dc_length, bar);
+        bulk_load_rows(s.line + (warp * 2 + parity) * kTile, group_line(a, group, warp), c.line, nr, a.dc_length, bar);
         if (warp == PROD - 1) {
-            const int sx = (int) (((long long) a.pos_x + row0 + a.dx_length - (2 * a.dc_length - 2)) % a.dx_length);
-            bulk_load_rows(s.dx + parity * kTile, group_dx(a, group), sx, nr, a.dx_length, bar);
+            bulk_load_rows(s.dx + parity * kTile, group_dx(a, group), c.dx_load, nr, a.dx_length, bar);
         }
+    }
+}
+
+// A sample enters the clock's ring: row `pos` and, for the first kMirror rows, its copy behind the end.
+__device__ __forceinline__ void ring_put(float *ring_lane, int pos, int ring_slots, float v) {
+    ring_lane[pos * 32] = v;
+    if (pos < kMirror) {
+        ring_lane[(pos + ring_slots) * 32] = v;
     }
 }
 
@@ -193,7 +226,7 @@ __device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layou
 // FULL blocks carry no per-row guards, so the 32 rows form one basic block that ptxas interleaves freely.
 template <int PROD, bool FULL>
 __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Layout &s, int warp, int lane, int group, int b,
-                                               int nr, int history, float &sum, float rcp) {
+                                               int nr, const Cursors &c, float &sum, float rcp) {
     const bool has_dc = PROD == 4;
     const int ring_mask = a.ring_slots - 1;
     const int row0 = b * kBlockRows;
@@ -205,7 +238,7 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                ring_lane[((history + row0 + r) & ring_mask) * 32] = src[r * 32];
+                ring_put(ring_lane, (row0 + r) & ring_mask, a.ring_slots, src[r * 32]);
             }
         }
         return;
@@ -214,11 +247,9 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
     // (slots are distinct: L >= 32) and, for the first stage, to the group delay line, which is 2L - 2 + 256 slots long
     // so that these writes never reach what the last stage still has to read
     if (lane == 0) {
-        const int slot = (int) (((long long) a.pos_l + row0) % a.dc_length);
-        bulk_store_rows(group_line(a, group, warp), in_tile, slot, nr, a.dc_length);
+        bulk_store_rows(group_line(a, group, warp), in_tile, c.line, nr, a.dc_length);
         if (warp == 0) {
-            const int sx = (int) (((long long) a.pos_x + row0) % a.dx_length);
-            bulk_store_rows(group_dx(a, group), in_tile, sx, nr, a.dx_length);
+            bulk_store_rows(group_dx(a, group), in_tile, c.dx_store, nr, a.dx_length);
         }
         bulk_commit();
     }
@@ -239,30 +270,39 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
             y[r] = sum;
         }
     }
-    float *dst = warp < PROD - 1 ? s.pipe + (warp * 2 + parity) * kTile + lane : nullptr;
-    const float *xd = s.dx + parity * kTile + lane;
+    // All 32 quotients first, as pure arithmetic: 32 independent FMUL + 4 FFMA chains that ptxas interleaves. (With the
+    // stores and the stage test inside this loop every row became its own basic block behind a branch, the chains ran one
+    // after the other through the same two registers and a block took 5600 cycles instead of a few hundred.)
+    float q[kBlockRows];
     bool redo = false;
 #pragma unroll
     for (int r = 0; r < kBlockRows; r++) {
         if (FULL || r < nr) {
-            const float q = div_by_length(y[r], length_f, rcp, redo);
-            if (warp < PROD - 1) {
-                dst[r * 32] = q;
-            } else {
-                ring_lane[((history + row0 + r) & ring_mask) * 32] = __fsub_rn(xd[r * 32], q);
-            }
+            q[r] = div_by_length(y[r], length_f, rcp, redo);
         }
     }
     if (__any_sync(0xffffffffu, redo)) {
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                const float q = __fdiv_rn(y[r], length_f);
-                if (warp < PROD - 1) {
-                    dst[r * 32] = q;
-                } else {
-                    ring_lane[((history + row0 + r) & ring_mask) * 32] = __fsub_rn(xd[r * 32], q);
-                }
+                q[r] = __fdiv_rn(y[r], length_f);
+            }
+        }
+    }
+    if (warp < PROD - 1) {
+        float *dst = s.pipe + (warp * 2 + parity) * kTile + lane;
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            if (FULL || r < nr) {
+                dst[r * 32] = q[r];
+            }
+        }
+    } else {
+        const float *xd = s.dx + parity * kTile + lane;
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            if (FULL || r < nr) {
+                ring_put(ring_lane, (row0 + r) & ring_mask, a.ring_slots, __fsub_rn(xd[r * 32], q[r]));
             }
         }
     }
@@ -279,7 +319,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
     Layout s;
     s.taps = smem;
     s.ring = s.taps + kTapsFloats;
-    s.pipe = s.ring + (size_t) a.ring_slots * 32;
+    s.pipe = s.ring + (size_t) (a.ring_slots + kMirror) * 32;
     s.rows = s.pipe + (PROD - 1) * 2 * kTile;
     s.line = s.rows + 2 * kTile;
     s.dx = s.line + PROD * 2 * kTile;
@@ -307,9 +347,11 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
     if (history > max_carry) {  // cannot happen unless a previous call already raised the error flag
         history = max_carry;
     }
+    // Ring position of working-buffer index i (0 = oldest carried sample) is (i - history) & mask: this call's row n sits at
+    // n & mask for every lane, whatever the lane carried over, so the producers' stores are uniform across the warp.
     if (warp == PROD) {
         for (int k = 0; k < history; k++) {
-            ring_lane[(k & ring_mask) * 32] = a.carry[(size_t) k * a.delay_stride + ch];
+            ring_put(ring_lane, (k - history) & ring_mask, a.ring_slots, a.carry[(size_t) k * a.delay_stride + ch]);
         }
     }
     const int n_blocks = (a.n_rows + kBlockRows - 1) / kBlockRows;
@@ -323,6 +365,10 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
         sum = a.sums[(size_t) warp * a.delay_stride + ch];
         rcp = __frcp_rn((float) a.dc_length);
     }
+    Cursors cur;
+    cur.line = has_dc ? (int) (a.pos_l % a.dc_length) : 0;
+    cur.dx_store = has_dc ? (int) (a.pos_x % a.dx_length) : 0;
+    cur.dx_load = has_dc ? (int) ((a.pos_x + a.dx_length - (2 * a.dc_length - 2)) % a.dx_length) : 0;
     // a block's delay-line slots may be fetched one block ahead only if the previous block does not write them
     const bool lookahead = !has_dc || a.dc_length >= 2 * kBlockRows;
     const int store_slack = has_dc ? max(0, min(2, (a.dc_length - 2 * kBlockRows) / kBlockRows)) : 0;
@@ -347,18 +393,20 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
             const int b = t - warp;
             if (b >= 0 && b < n_blocks) {
                 const int nr = min(kBlockRows, a.n_rows - b * kBlockRows);
+                const Cursors nxt = next_block(a, cur);
                 if (b == 0 || !lookahead) {
-                    fetch_block<PROD>(a, s, warp, lane, blockIdx.x, b);
+                    fetch_block<PROD>(a, s, warp, lane, blockIdx.x, b, cur);
                 }
                 if (lookahead && b + 1 < n_blocks) {
-                    fetch_block<PROD>(a, s, warp, lane, blockIdx.x, b + 1);
+                    fetch_block<PROD>(a, s, warp, lane, blockIdx.x, b + 1, nxt);
                 }
                 mbar_wait(s.bars + warp * 2 + (b & 1), (uint32_t) ((b >> 1) & 1));
                 if (nr == kBlockRows) {
-                    producer_block<PROD, true>(a, s, warp, lane, blockIdx.x, b, nr, history, sum, rcp);
+                    producer_block<PROD, true>(a, s, warp, lane, blockIdx.x, b, nr, cur, sum, rcp);
                 } else {
-                    producer_block<PROD, false>(a, s, warp, lane, blockIdx.x, b, nr, history, sum, rcp);
+                    producer_block<PROD, false>(a, s, warp, lane, blockIdx.x, b, nr, cur, sum, rcp);
                 }
+                cur = nxt;
                 // this block's delay-line stores are done before the step ends: their source tile is recycled two steps
                 // later and the lines are read again at the earliest one block later
                 if (lane == 0) {
@@ -369,47 +417,54 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
             // Mueller & Mueller loop over everything the last producer finished before this step
             const int done_blocks = t - PROD + 1;
             const int avail = history + (done_blocks <= 0 ? 0 : min(a.n_rows, done_blocks * kBlockRows));
+            // The body is branch-free: the reference's three data-dependent paths (leading zero taps, NaN output, loop
+            // update) are computed side by side and selected, so that lanes in different situations stay converged and the
+            // iteration is one dependent chain of ~40 operations instead of a sequence of divergent regions.
             while (run_clock && ii >= 0 && ii + 7 < avail && oo < a.max_out) {
                 if (avail + kBlockRows - (ii - 3) > a.ring_slots) {  // the lane fell behind its ring (pathological input)
                     overflow = true;
                     break;
                 }
                 const int imu = __float2int_rn(__fmul_rn(mu, 128.0f));
-                const float *tp = s.taps + imu * 8;
-                // aligned dot product of fir_filter_process_float_single: (ii & 3) earlier samples meet zero taps first
+                const float4 t_lo = *reinterpret_cast<const float4 *>(s.taps + imu * 8);
+                const float4 t_hi = *reinterpret_cast<const float4 *>(s.taps + imu * 8 + 4);
+                const float tp[8] = {t_lo.x, t_lo.y, t_lo.z, t_lo.w, t_hi.x, t_hi.y, t_hi.z, t_hi.w};
+                // 11 samples from ii - 3 on; the mirror rows make the window contiguous
+                const float *win = ring_lane + ((ii - 3 - history) & ring_mask) * 32;
+                float v[11];
+#pragma unroll
+                for (int k = 0; k < 11; k++) {
+                    v[k] = win[k * 32];
+                }
+                // aligned dot product of fir_filter_process_float_single: (ii & 3) earlier samples meet zero taps first.
+                // Their products are +-0, or NaN for a non-finite sample; a skipped product is replaced by +0, which leaves
+                // the accumulator (+0, or already NaN) unchanged.
                 const int lead = ii & 3;
                 float acc = 0.0f;
-                if (lead >= 3) acc = dot_step(a.fast, acc, ring_lane[((ii - 3) & ring_mask) * 32], 0.0f);
-                if (lead >= 2) acc = dot_step(a.fast, acc, ring_lane[((ii - 2) & ring_mask) * 32], 0.0f);
-                if (lead >= 1) acc = dot_step(a.fast, acc, ring_lane[((ii - 1) & ring_mask) * 32], 0.0f);
+                acc = dot_step(a.fast, acc, lead >= 3 ? v[0] : 0.0f, 0.0f);
+                acc = dot_step(a.fast, acc, lead >= 2 ? v[1] : 0.0f, 0.0f);
+                acc = dot_step(a.fast, acc, lead >= 1 ? v[2] : 0.0f, 0.0f);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    acc = dot_step(a.fast, acc, ring_lane[((ii + k) & ring_mask) * 32], tp[7 - k]);
+                    acc = dot_step(a.fast, acc, v[3 + k], tp[7 - k]);
                 }
-                float out = acc;
-                if (isnan(out)) {  // clock_recovery_mm.c:107-113
-                    out = 0.0f;
-                    if (soft != nullptr) soft[oo] = out;
-                    if (hard != nullptr) hard[oo] = 0;
-                    previous = ii;
-                    ii += (int) floorf(omega);
-                    oo++;
-                    continue;
-                }
+                const bool nan = isnan(acc);  // clock_recovery_mm.c:107-113: output 0, skip the loop update
+                const float out = nan ? 0.0f : acc;
                 if (soft != nullptr) soft[oo] = out;
                 if (hard != nullptr) {
-                    const float scaled = __fmul_rn(out, 127.0f);
-                    hard[oo] = scaled > 127.0f ? (int8_t) 127 : (scaled < -128.0f ? (int8_t) -128 : (int8_t) __float2int_rn(scaled));
+                    const float scaled = fminf(fmaxf(__fmul_rn(out, 127.0f), -128.0f), 127.0f);
+                    hard[oo] = (int8_t) __float2int_rn(scaled);
                 }
                 const float mm_val = __fsub_rn(__fmul_rn(slice_pm1(last_sample), out), __fmul_rn(slice_pm1(out), last_sample));
-                last_sample = out;
+                float omega_next = __fadd_rn(omega, __fmul_rn(a.gain_omega, mm_val));
+                omega_next = __fadd_rn(a.omega_mid, branchless_clip(__fsub_rn(omega_next, a.omega_mid), a.omega_lim));
+                const float mu_next = __fadd_rn(__fadd_rn(mu, omega_next), __fmul_rn(a.gain_mu, mm_val));
+                const float whole = floorf(nan ? omega : mu_next);
                 previous = ii;
-                omega = __fadd_rn(omega, __fmul_rn(a.gain_omega, mm_val));
-                omega = __fadd_rn(a.omega_mid, branchless_clip(__fsub_rn(omega, a.omega_mid), a.omega_lim));
-                mu = __fadd_rn(__fadd_rn(mu, omega), __fmul_rn(a.gain_mu, mm_val));
-                const float whole = floorf(mu);
                 ii += (int) whole;
-                mu = __fsub_rn(mu, whole);
+                last_sample = nan ? last_sample : out;
+                mu = nan ? mu : __fsub_rn(mu_next, whole);
+                omega = nan ? omega : omega_next;
                 oo++;
             }
         }
@@ -442,7 +497,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
         atomicOr(a.error_flag, 2);  // symbol capacity reached with input left over
     }
     for (int k = 0; k < (int) carried; k++) {
-        a.carry[(size_t) k * a.delay_stride + ch] = ring_lane[(((int) last_index + k) & ring_mask) * 32];
+        a.carry[(size_t) k * a.delay_stride + ch] = ring_lane[(((int) last_index + k - history) & ring_mask) * 32];
     }
     sdrm_clock_state next;
     next.mu = mu;
@@ -508,7 +563,7 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
     cudaStream_t stream = (cudaStream_t) stream_ptr;
     const int blocks = (args->n_ch + 31) / 32;
     const int prod = has_dc ? 4 : 1;
-    const size_t floats = (size_t) kTapsFloats + (size_t) args->ring_slots * 32 + (size_t) (prod - 1) * 2 * kTile + 2 * kTile +
+    const size_t floats = (size_t) kTapsFloats + (size_t) (args->ring_slots + kMirror) * 32 + (size_t) (prod - 1) * 2 * kTile + 2 * kTile +
                           (size_t) prod * 2 * kTile + 2 * kTile;
     const size_t smem = floats * sizeof(float) + (size_t) prod * 2 * sizeof(uint64_t);
     void (*kernel)(const sdrm_tail_args) = has_dc ? demod_tail_kernel<4> : demod_tail_kernel<1>;

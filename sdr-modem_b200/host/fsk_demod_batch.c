@@ -418,6 +418,9 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     ca.out_stride = b->out_stride;
     ca.out_len = b->d_out_len[slot];
     ca.max_out = (int) (b->cfg.max_symbols_per_call != 0 ? b->cfg.max_symbols_per_call : b->cfg.max_input_buffer_length);
+    if (b->cfg.flags & 0x40000000u) {
+        ca.max_out = 0; /* measurement aid: the clock loop never runs (results are invalid) */
+    }
     ca.error_flag = b->d_error;
     ca.fast = b->fast;
     if (b->dc_len > 0) {
