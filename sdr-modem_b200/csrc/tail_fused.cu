@@ -95,6 +95,20 @@ __device__ __forceinline__ void bulk_store_rows(float *gmem_rows, const float *s
     }
 }
 
+// one lane of a converged warp, chosen by the hardware: the compiler then issues the bulk copies from uniform registers
+// without the per-thread "waterfall" loop it builds around `if (lane == 0)`
+__device__ __forceinline__ bool elect_one() {
+    uint32_t is_leader;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(is_leader));
+    return is_leader != 0;
+}
+
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
 // End-of-step wait of the lane that issued a block's bulk stores. The stores have finished READING their shared-memory
@@ -125,18 +139,21 @@ __device__ __forceinline__ float dot_step(bool fast, float acc, float v, float t
 }
 
 // sum / L, correctly rounded, for a constant L with rcp = RN(1/L): two Markstein corrections of q0 = RN(sum * rcp).
-// `redo` is raised outside the exponent range where the residuals are exact; the caller then uses __fdiv_rn.
-__device__ __forceinline__ float div_by_length(float sum, float length_f, float rcp, bool &redo) {
+// Valid inside the exponent range where the residuals are exact (see outside_fast_division_range).
+// A zero sum: +0 gives q0 = e0 = q1 = ... = +0. (-0 would come back as +0, but the running sums of this kernel are never -0:
+// they start at +0 and RN(x + (-x)) = +0; the per-block dc_blocker handle in tail.cu keeps an explicit test.)
+__device__ __forceinline__ float div_by_length(float sum, float length_f, float rcp) {
     const float q0 = __fmul_rn(sum, rcp);
     const float e0 = __fmaf_rn(-q0, length_f, sum);
     const float q1 = __fmaf_rn(e0, rcp, q0);
     const float e1 = __fmaf_rn(-q1, length_f, sum);
-    const float q2 = __fmaf_rn(e1, rcp, q1);
+    return __fmaf_rn(e1, rcp, q1);
+}
+
+// sums for which div_by_length is not proven (huge, non-finite, or tiny but non-zero): the caller uses __fdiv_rn
+__device__ __forceinline__ bool outside_fast_division_range(float sum) {
     const float mag = fabsf(sum);
-    redo |= !(mag < 1.0e18f) || (mag < 1.0e-18f && sum != 0.0f);
-    // a zero sum: +0 gives q0 = e0 = q1 = ... = +0. (-0 would come back as +0, but the running sums of this kernel are never
-    // -0: they start at +0 and RN(x + (-x)) = +0; the per-block dc_blocker handle in tail.cu keeps the explicit test.)
-    return q2;
+    return !(mag < 1.0e18f) || (mag < 1.0e-18f && sum != 0.0f);
 }
 
 // Shared-memory map of one CTA.
@@ -165,6 +182,14 @@ __device__ __forceinline__ float *group_dx(const sdrm_tail_args &a, int group) {
 // One elected lane fetches block b for this warp's stage: its rows of the TC ring (warp 0), the stage's own inputs of L
 // rows ago (its delay line) and, for the last stage, x[n - (2L - 2)] from the group delay line. Completion is counted on
 // the warp's mbarrier of parity b & 1.
+// The group's slices of the global arrays a producer warp touches, resolved once per kernel (recomputing the 64-bit
+// addresses for every copy was most of what the elected lane did).
+struct Arrays {
+    const float *rows;  // lpf2 output ring (first stage)
+    float *line;        // this stage's delay line
+    float *dx;          // group delay line (first stage writes, last stage reads)
+};
+
 // Cursors of a producer warp into the circular arrays, for the block it is working on. They advance by one block per
 // step with a compare-and-subtract (all lengths are >= 32 rows); a 64-bit modulo per copy, as a first version had, was a
 // quarter of all instructions the kernel executed, on one lane, in front of everything else.
@@ -188,9 +213,9 @@ __device__ __forceinline__ Cursors next_block(const sdrm_tail_args &a, const Cur
 }
 
 template <int PROD>
-__device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layout &s, int warp, int lane, int group, int b,
+__device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layout &s, const Arrays &g, int warp, int lane, int b,
                                             const Cursors &c) {
-    if (lane != 0) {
+    if (!elect_one()) {
         return;
     }
     const bool has_dc = PROD == 4;
@@ -202,12 +227,12 @@ __device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layou
     mbar_expect_tx(bar, (uint32_t) (copies * nr * kRowBytes));
     if (warp == 0) {
         const int first = (int) ((a.head + row0) & (a.ring_rows - 1));
-        bulk_load_rows(s.rows + parity * kTile, group_rows(a, group), first, nr, a.ring_rows, bar);
+        bulk_load_rows(s.rows + parity * kTile, g.rows, first, nr, a.ring_rows, bar);
     }
     if (has_dc) {
-        bulk_load_rows(s.line + (warp * 2 + parity) * kTile, group_line(a, group, warp), c.line, nr, a.dc_length, bar);
+        bulk_load_rows(s.line + (warp * 2 + parity) * kTile, g.line, c.line, nr, a.dc_length, bar);
         if (warp == PROD - 1) {
-            bulk_load_rows(s.dx + parity * kTile, group_dx(a, group), c.dx_load, nr, a.dx_length, bar);
+            bulk_load_rows(s.dx + parity * kTile, g.dx, c.dx_load, nr, a.dx_length, bar);
         }
     }
 }
@@ -225,7 +250,7 @@ __device__ __forceinline__ void ring_put(float *ring_lane, int pos, int ring_slo
 //   last stage      x[n-(2L-2)] - y4 appended to the clock's sample ring              (dc_blocker.c:110-114)
 // FULL blocks carry no per-row guards, so the 32 rows form one basic block that ptxas interleaves freely.
 template <int PROD, bool FULL>
-__device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Layout &s, int warp, int lane, int group, int b,
+__device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Layout &s, const Arrays &g, int warp, int lane, int b,
                                                int nr, const Cursors &c, float &sum, float rcp) {
     const bool has_dc = PROD == 4;
     const int ring_mask = a.ring_slots - 1;
@@ -233,12 +258,22 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
     const int parity = b & 1;
     const float *in_tile = warp == 0 ? s.rows + parity * kTile : s.pipe + ((warp - 1) * 2 + parity) * kTile;
     const float *src = in_tile + lane;
-    float *ring_lane = s.ring + lane;
+    // this block's 32 rows of the clock's ring: aligned to the block size, so they never wrap (ring_slots is a power of two)
+    float *ring_block = s.ring + lane + (row0 & ring_mask) * 32;
+    const bool mirrored = (row0 & ring_mask) == 0;  // rows [0, kMirror) are stored a second time behind the ring's end
     if (!has_dc) {
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                ring_put(ring_lane, (row0 + r) & ring_mask, a.ring_slots, src[r * 32]);
+                ring_block[r * 32] = src[r * 32];
+            }
+        }
+        if (mirrored) {
+#pragma unroll
+            for (int r = 0; r < kMirror; r++) {
+                if (FULL || r < nr) {
+                    ring_block[(r + a.ring_slots) * 32] = src[r * 32];
+                }
             }
         }
         return;
@@ -246,10 +281,10 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
     // the block's own inputs replace the ones it is about to consume: the input tile goes back to the stage's delay line
     // (slots are distinct: L >= 32) and, for the first stage, to the group delay line, which is 2L - 2 + 256 slots long
     // so that these writes never reach what the last stage still has to read
-    if (lane == 0) {
-        bulk_store_rows(group_line(a, group, warp), in_tile, c.line, nr, a.dc_length);
+    if (elect_one()) {  // always the same lane for the full mask: it owns the warp's bulk groups
+        bulk_store_rows(g.line, in_tile, c.line, nr, a.dc_length);
         if (warp == 0) {
-            bulk_store_rows(group_dx(a, group), in_tile, c.dx_store, nr, a.dx_length);
+            bulk_store_rows(g.dx, in_tile, c.dx_store, nr, a.dx_length);
         }
         bulk_commit();
     }
@@ -270,22 +305,40 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
             y[r] = sum;
         }
     }
-    // All 32 quotients first, as pure arithmetic: 32 independent FMUL + 4 FFMA chains that ptxas interleaves. (With the
-    // stores and the stage test inside this loop every row became its own basic block behind a branch, the chains ran one
-    // after the other through the same two registers and a block took 5600 cycles instead of a few hundred.)
-    float q[kBlockRows];
-    bool redo = false;
-#pragma unroll
-    for (int r = 0; r < kBlockRows; r++) {
-        if (FULL || r < nr) {
-            q[r] = div_by_length(y[r], length_f, rcp, redo);
-        }
-    }
-    if (__any_sync(0xffffffffu, redo)) {
+    // The last stage also needs x[n - (2L - 2)]: fetched now, while registers are free, so that the loads are not strung
+    // between the stores at the end (they were: LDS, FADD, STS one after the other, 35 cycles a row).
+    float xv[kBlockRows];
+    if (warp == PROD - 1) {
+        const float *xd = s.dx + parity * kTile + lane;
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                q[r] = __fdiv_rn(y[r], length_f);
+                xv[r] = xd[r * 32];
+            }
+        }
+    }
+    // All 32 quotients as pure arithmetic, in place: 32 independent FMUL + 4 FFMA chains that ptxas interleaves. (With the
+    // stores and the stage test inside this loop every row became its own basic block behind a branch, the chains ran one
+    // after the other through the same two registers and a block took 5600 cycles instead of a few hundred.)
+    bool exact = false;
+#pragma unroll
+    for (int r = 0; r < kBlockRows; r++) {
+        if (FULL || r < nr) {
+            exact |= outside_fast_division_range(y[r]);
+        }
+    }
+    if (__any_sync(0xffffffffu, exact)) {
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            if (FULL || r < nr) {
+                y[r] = __fdiv_rn(y[r], length_f);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            if (FULL || r < nr) {
+                y[r] = div_by_length(y[r], length_f, rcp);
             }
         }
     }
@@ -294,15 +347,23 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                dst[r * 32] = q[r];
+                dst[r * 32] = y[r];
             }
         }
     } else {
-        const float *xd = s.dx + parity * kTile + lane;
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                ring_put(ring_lane, (row0 + r) & ring_mask, a.ring_slots, __fsub_rn(xd[r * 32], q[r]));
+                y[r] = __fsub_rn(xv[r], y[r]);
+                ring_block[r * 32] = y[r];
+            }
+        }
+        if (mirrored) {
+#pragma unroll
+            for (int r = 0; r < kMirror; r++) {
+                if (FULL || r < nr) {
+                    ring_block[(r + a.ring_slots) * 32] = y[r];
+                }
             }
         }
     }
@@ -365,6 +426,10 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
         sum = a.sums[(size_t) warp * a.delay_stride + ch];
         rcp = __frcp_rn((float) a.dc_length);
     }
+    Arrays arrays;
+    arrays.rows = group_rows(a, blockIdx.x);
+    arrays.line = has_dc ? group_line(a, blockIdx.x, warp < PROD ? warp : 0) : nullptr;
+    arrays.dx = has_dc ? group_dx(a, blockIdx.x) : nullptr;
     Cursors cur;
     cur.line = has_dc ? (int) (a.pos_l % a.dc_length) : 0;
     cur.dx_store = has_dc ? (int) (a.pos_x % a.dx_length) : 0;
@@ -395,21 +460,21 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                 const int nr = min(kBlockRows, a.n_rows - b * kBlockRows);
                 const Cursors nxt = next_block(a, cur);
                 if (b == 0 || !lookahead) {
-                    fetch_block<PROD>(a, s, warp, lane, blockIdx.x, b, cur);
+                    fetch_block<PROD>(a, s, arrays, warp, lane, b, cur);
                 }
                 if (lookahead && b + 1 < n_blocks) {
-                    fetch_block<PROD>(a, s, warp, lane, blockIdx.x, b + 1, nxt);
+                    fetch_block<PROD>(a, s, arrays, warp, lane, b + 1, nxt);
                 }
                 mbar_wait(s.bars + warp * 2 + (b & 1), (uint32_t) ((b >> 1) & 1));
                 if (nr == kBlockRows) {
-                    producer_block<PROD, true>(a, s, warp, lane, blockIdx.x, b, nr, cur, sum, rcp);
+                    producer_block<PROD, true>(a, s, arrays, warp, lane, b, nr, cur, sum, rcp);
                 } else {
-                    producer_block<PROD, false>(a, s, warp, lane, blockIdx.x, b, nr, cur, sum, rcp);
+                    producer_block<PROD, false>(a, s, arrays, warp, lane, b, nr, cur, sum, rcp);
                 }
                 cur = nxt;
                 // this block's delay-line stores are done before the step ends: their source tile is recycled two steps
                 // later and the lines are read again at the earliest one block later
-                if (lane == 0) {
+                if (elect_one()) {  // always the same lane for the full mask: it owns the warp's bulk groups
                     bulk_wait_step(store_slack);
                 }
             }
@@ -523,8 +588,8 @@ __global__ void div_selftest_kernel(int length, uint32_t seed, int per_thread, u
         const uint32_t expo = 69u + (x >> 8) % 117u;
         const uint32_t bits = (x & 0x807FFFFFu) | (expo << 23);
         const float sum = __uint_as_float(bits);
-        bool redo = false;
-        const float fast = div_by_length(sum, length_f, rcp, redo);
+        const bool redo = outside_fast_division_range(sum);
+        const float fast = div_by_length(sum, length_f, rcp);
         const float exact = __fdiv_rn(sum, length_f);
         if (redo || __float_as_uint(fast) != __float_as_uint(exact)) {
             bad++;
