@@ -364,7 +364,7 @@ def main():
                      "call_unpipelined": float(np.mean(call_ms))},
     }
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
         cpu = cpu_reference_run(shape, args.cpu_seconds)
         if cpu is not None:
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
