@@ -309,7 +309,7 @@ def main():
             e2e_s = float(t.item())
         symbols = int(pin_len[0].array.sum())
         e2e = {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": n_ch * chunk * 8, "d2h_bytes_per_step": n_ch * cap + n_ch * 4,
+               "h2d_bytes_per_step": world * n_ch * chunk * 8, "d2h_bytes_per_step": world * (n_ch * cap + n_ch * 4),
                "steps": e2e_steps, "symbols_last_step": symbols}
         # the same stream as 12-bit int16 IQ (what the PlutoSDR hands over, plutosdr.c:129), converted on the device:
         # half the host->device bytes. Reported beside the cf32 figure, which stays the headline (the reference API is cf32).
@@ -333,7 +333,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e16_s = float(t.item())
         e2e["int16_ingest"] = {"value": samples_per_step * e2e_steps / e2e16_s / 1e6, "unit": UNIT,
-                               "h2d_bytes_per_step": n_ch * chunk * 4, "symbols_last_step": int(pin_len[0].array.sum())}
+                               "h2d_bytes_per_step": world * n_ch * chunk * 4, "symbols_last_step": int(pin_len[0].array.sum())}
         for a in pin_in + pin_out + pin_len + pin_in16:
             a.close()
 

@@ -175,11 +175,17 @@ int sdrm_gfsk_mod_batch_process(sdrm_gfsk_mod_batch *batch, const uint8_t *input
  * [channels][out_stride pairs] = saturate(rint(v * scalar)), scalar = 32768 */
 int sdrm_gfsk_mod_batch_process_i16(sdrm_gfsk_mod_batch *batch, const uint8_t *input, size_t in_stride, size_t input_len,
                                     int16_t *output, size_t out_stride, float scalar, size_t *output_len);
-/* device buffers, asynchronous on the batch's stream; d_output rows must be 8-byte aligned */
+/*
+ * Device buffers, asynchronous; d_output rows must be 8-byte aligned. A call is three stages on three streams (shaping,
+ * phase walk, trigonometry) so that consecutive calls overlap: d_input is consumed on sdrm_gfsk_mod_batch_input_stream
+ * (order its producer before that stream, or have it ready when the call is made), d_output is complete on
+ * sdrm_gfsk_mod_batch_stream. Two calls may be in flight; give them different output buffers.
+ */
 int sdrm_gfsk_mod_batch_process_device(sdrm_gfsk_mod_batch *batch, const void *d_input, size_t in_stride, size_t input_len,
                                        void *d_output, size_t out_stride);
 int sdrm_gfsk_mod_batch_sync(sdrm_gfsk_mod_batch *batch);
 void *sdrm_gfsk_mod_batch_stream(sdrm_gfsk_mod_batch *batch);
+void *sdrm_gfsk_mod_batch_input_stream(sdrm_gfsk_mod_batch *batch);
 uint64_t sdrm_gfsk_mod_batch_launch_count(const sdrm_gfsk_mod_batch *batch);
 void sdrm_gfsk_mod_batch_destroy(sdrm_gfsk_mod_batch *batch);
 

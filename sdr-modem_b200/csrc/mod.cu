@@ -418,29 +418,48 @@ extern "C" int sdrm_cu_interp_fir(const sdrm_interp_args *a, void *stream_ptr) {
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }
 
-extern "C" int sdrm_cu_freq_mod(float *work, size_t rows, float *phase_state, void *out, size_t out_stride, long long n, int n_ch,
-                                void *stream_ptr) {
+extern "C" int sdrm_cu_phase_walk(float *work, size_t rows, float *phase_state, long long n, int n_ch, void *stream_ptr) {
     if (n <= 0 || n_ch <= 0) {
         return 0;
     }
     if ((long long) rows < n || ((uintptr_t) work & 127) != 0) {
         return -22;
     }
-    cudaStream_t stream = (cudaStream_t) stream_ptr;
-    const int groups = (n_ch + 31) / 32;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(phase_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem);
         configured = true;
     }
-    phase_walk_kernel<<<groups, 32, kWalkSmem, stream>>>(work, rows, phase_state, n, n_ch);
+    phase_walk_kernel<<<(n_ch + 31) / 32, 32, kWalkSmem, (cudaStream_t) stream_ptr>>>(work, rows, phase_state, n, n_ch);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}
+
+extern "C" int sdrm_cu_phase_to_iq(const float *work, size_t rows, void *out, size_t out_stride, long long n, int n_ch,
+                                   void *stream_ptr) {
+    if (n <= 0 || n_ch <= 0) {
+        return 0;
+    }
+    if ((long long) rows < n) {
+        return -22;
+    }
+    const int groups = (n_ch + 31) / 32;
     long long bx = (n + kTileRows - 1) / kTileRows;
     const long long want = (148LL * 8 + groups - 1) / groups;
     if (bx > want) {
         bx = want;
     }
     dim3 grid((unsigned) bx, (unsigned) groups);
-    phase_to_iq_kernel<<<grid, 256, 0, stream>>>(work, rows, (float2 *) out, out_stride, n, n_ch);
+    phase_to_iq_kernel<<<grid, 256, 0, (cudaStream_t) stream_ptr>>>(work, rows, (float2 *) out, out_stride, n, n_ch);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
+}
+
+extern "C" int sdrm_cu_freq_mod(float *work, size_t rows, float *phase_state, void *out, size_t out_stride, long long n, int n_ch,
+                                void *stream_ptr) {
+    int code = sdrm_cu_phase_walk(work, rows, phase_state, n, n_ch, stream_ptr);
+    if (code != 0) {
+        return code;
+    }
+    return sdrm_cu_phase_to_iq(work, rows, out, out_stride, n, n_ch, stream_ptr);
 }

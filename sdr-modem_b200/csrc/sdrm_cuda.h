@@ -216,6 +216,9 @@ int sdrm_cu_interp_fir(const sdrm_interp_args *args, void *stream);
  */
 int sdrm_cu_freq_mod(float *work, size_t rows, float *phase_state, void *out, size_t out_stride, long long n, int n_ch,
                      void *stream);
+/* the two halves of sdrm_cu_freq_mod, for callers that pipeline them on different streams */
+int sdrm_cu_phase_walk(float *work, size_t rows, float *phase_state, long long n, int n_ch, void *stream);
+int sdrm_cu_phase_to_iq(const float *work, size_t rows, void *out, size_t out_stride, long long n, int n_ch, void *stream);
 
 /*
  * SDR sample formats (reference src/sdr/plutosdr.c:83,129, VOLK generic kernels): int16 (I, Q) pairs <-> float2 rows.

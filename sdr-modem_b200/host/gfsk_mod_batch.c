@@ -69,7 +69,7 @@ struct sdrm_gfsk_mod_batch_t {
     float *d_taps_rev;
     float *d_history; /* [n_ch][branch_taps - 1] */
     float *d_phase;   /* [n_ch] */
-    float *d_work;    /* GTC layout [groups][work_rows][32]: increments, then phases, in place */
+    float *d_work[2]; /* GTC layout [groups][work_rows][32]: increments, then phases, in place; one per call in flight */
     size_t work_rows;
     uint32_t n_groups;
     void *d_in;
@@ -77,7 +77,15 @@ struct sdrm_gfsk_mod_batch_t {
     void *d_out;
     void *d_out16; /* int16 pairs, process_i16 only */
     size_t out_stride_dev;
-    cudaStream_t stream;
+    /* three stages on three streams, so that call k's trigonometry, call k+1's phase walk and call k+2's shaping overlap:
+     * the walk is serial per channel and leaves most of the GPU idle */
+    cudaStream_t s_shape; /* input copy, bits -> shaped increments */
+    cudaStream_t s_walk;  /* float phase recurrence */
+    cudaStream_t stream;  /* phases -> cf32; the public stream: results are complete on it */
+    cudaEvent_t ev_shaped[2];
+    cudaEvent_t ev_walked[2];
+    cudaEvent_t ev_read[2]; /* the work buffer has been read out */
+    uint64_t calls;
     uint64_t launches;
 };
 
@@ -129,8 +137,22 @@ int sdrm_gfsk_mod_batch_create(uint32_t n_channels, float samples_per_symbol, fl
     b->n_groups = (n_channels + 31) / 32;
     if (code == 0) code = sdrm_dev_zalloc((void **) &b->d_history, (size_t) n_channels * (b->branch_taps > 1 ? b->branch_taps - 1 : 1) * sizeof(float));
     if (code == 0) code = sdrm_dev_zalloc((void **) &b->d_phase, n_channels * sizeof(float));
-    if (code == 0) code = sdrm_dev_zalloc((void **) &b->d_work, (size_t) b->n_groups * b->work_rows * 32 * sizeof(float));
-    if (code == 0) code = sdrm_cuda_code(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "stream");
+    for (int i = 0; i < 2 && code == 0; i++) {
+        code = sdrm_dev_zalloc((void **) &b->d_work[i], (size_t) b->n_groups * b->work_rows * 32 * sizeof(float));
+        if (code == 0) code = sdrm_cuda_code(cudaEventCreateWithFlags(&b->ev_shaped[i], cudaEventDisableTiming), "event");
+        if (code == 0) code = sdrm_cuda_code(cudaEventCreateWithFlags(&b->ev_walked[i], cudaEventDisableTiming), "event");
+        if (code == 0) code = sdrm_cuda_code(cudaEventCreateWithFlags(&b->ev_read[i], cudaEventDisableTiming), "event");
+    }
+    {
+        /* the walk has few, long-running blocks and the next call's shaping feeds it: both go ahead of the wide trigonometry
+         * kernel of the previous call, whose blocks would otherwise fill every SM first */
+        int least = 0;
+        int greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (code == 0) code = sdrm_cuda_code(cudaStreamCreateWithPriority(&b->s_shape, cudaStreamNonBlocking, greatest), "stream");
+        if (code == 0) code = sdrm_cuda_code(cudaStreamCreateWithPriority(&b->s_walk, cudaStreamNonBlocking, greatest), "stream");
+        if (code == 0) code = sdrm_cuda_code(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, least), "stream");
+    }
     if (code != 0) {
         sdrm_gfsk_mod_batch_destroy(b);
         return code;
@@ -153,16 +175,29 @@ static int mod_enqueue(sdrm_gfsk_mod_batch *b, const void *d_in, size_t in_strid
     a.history = b->d_history;
     a.apply_scale = 1;
     a.scale = b->sensitivity;
-    a.out = b->d_work;
+    const int slot = (int) (b->calls & 1);
+    float *work = b->d_work[slot];
+    a.out = work;
     a.out_stride = b->work_rows;
     a.out_grouped = 1;
-    int code = sdrm_launch_code(sdrm_cu_interp_fir(&a, b->stream), "gfsk shaping");
+    /* the work buffer of two calls ago has been read out */
+    SDRM_CUDA_TRY(cudaStreamWaitEvent(b->s_shape, b->ev_read[slot], 0));
+    int code = sdrm_launch_code(sdrm_cu_interp_fir(&a, b->s_shape), "gfsk shaping");
     if (code != 0) return code;
+    SDRM_CUDA_TRY(cudaEventRecord(b->ev_shaped[slot], b->s_shape));
     const long long n_out = (long long) n_bytes * 8 * b->interpolation;
-    code = sdrm_launch_code(sdrm_cu_freq_mod(b->d_work, b->work_rows, b->d_phase, d_out, out_stride, n_out, (int) b->n_ch, b->stream),
-                            "frequency modulator");
+    SDRM_CUDA_TRY(cudaStreamWaitEvent(b->s_walk, b->ev_shaped[slot], 0));
+    code = sdrm_launch_code(sdrm_cu_phase_walk(work, b->work_rows, b->d_phase, n_out, (int) b->n_ch, b->s_walk), "phase walk");
+    if (code != 0) return code;
+    SDRM_CUDA_TRY(cudaEventRecord(b->ev_walked[slot], b->s_walk));
+    SDRM_CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_walked[slot], 0));
+    code = sdrm_launch_code(sdrm_cu_phase_to_iq(work, b->work_rows, d_out, out_stride, n_out, (int) b->n_ch, b->stream),
+                            "phase to iq");
+    if (code != 0) return code;
+    SDRM_CUDA_TRY(cudaEventRecord(b->ev_read[slot], b->stream));
+    b->calls++;
     b->launches += 4;
-    return code;
+    return 0;
 }
 
 static int mod_check(const sdrm_gfsk_mod_batch *b, size_t n_bytes) {
@@ -198,7 +233,7 @@ int sdrm_gfsk_mod_batch_process(sdrm_gfsk_mod_batch *b, const uint8_t *input, si
         if (code != 0) return code;
     }
     if (input_len > 0) {
-        SDRM_CUDA_TRY(cudaMemcpy2DAsync(b->d_in, b->in_stride_dev, input, in_stride, input_len, b->n_ch, cudaMemcpyHostToDevice, b->stream));
+        SDRM_CUDA_TRY(cudaMemcpy2DAsync(b->d_in, b->in_stride_dev, input, in_stride, input_len, b->n_ch, cudaMemcpyHostToDevice, b->s_shape));
     }
     int code = mod_enqueue(b, b->d_in, b->in_stride_dev, input_len, b->d_out, b->out_stride_dev);
     if (code != 0) return code;
@@ -235,7 +270,7 @@ int sdrm_gfsk_mod_batch_process_i16(sdrm_gfsk_mod_batch *b, const uint8_t *input
         if (code != 0) return code;
     }
     if (input_len > 0) {
-        SDRM_CUDA_TRY(cudaMemcpy2DAsync(b->d_in, b->in_stride_dev, input, in_stride, input_len, b->n_ch, cudaMemcpyHostToDevice, b->stream));
+        SDRM_CUDA_TRY(cudaMemcpy2DAsync(b->d_in, b->in_stride_dev, input, in_stride, input_len, b->n_ch, cudaMemcpyHostToDevice, b->s_shape));
     }
     int code = mod_enqueue(b, b->d_in, b->in_stride_dev, input_len, b->d_out, b->out_stride_dev);
     if (code != 0) return code;
@@ -260,9 +295,13 @@ int sdrm_gfsk_mod_batch_sync(sdrm_gfsk_mod_batch *b) {
         return -1;
     }
     SDRM_CUDA_TRY(cudaSetDevice(b->device));
+    SDRM_CUDA_TRY(cudaStreamSynchronize(b->s_shape));
+    SDRM_CUDA_TRY(cudaStreamSynchronize(b->s_walk));
     SDRM_CUDA_TRY(cudaStreamSynchronize(b->stream));
     return 0;
 }
+
+void *sdrm_gfsk_mod_batch_input_stream(sdrm_gfsk_mod_batch *b) { return b == NULL ? NULL : (void *) b->s_shape; }
 
 void *sdrm_gfsk_mod_batch_stream(sdrm_gfsk_mod_batch *b) { return b == NULL ? NULL : (void *) b->stream; }
 
@@ -273,14 +312,22 @@ void sdrm_gfsk_mod_batch_destroy(sdrm_gfsk_mod_batch *b) {
         return;
     }
     cudaSetDevice(b->device);
-    if (b->stream != NULL) {
-        cudaStreamSynchronize(b->stream);
-        cudaStreamDestroy(b->stream);
+    cudaStream_t streams[3] = {b->s_shape, b->s_walk, b->stream};
+    for (int i = 0; i < 3; i++) {
+        if (streams[i] != NULL) {
+            cudaStreamSynchronize(streams[i]);
+            cudaStreamDestroy(streams[i]);
+        }
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaFree(b->d_work[i]);
+        if (b->ev_shaped[i] != NULL) cudaEventDestroy(b->ev_shaped[i]);
+        if (b->ev_walked[i] != NULL) cudaEventDestroy(b->ev_walked[i]);
+        if (b->ev_read[i] != NULL) cudaEventDestroy(b->ev_read[i]);
     }
     cudaFree(b->d_taps_rev);
     cudaFree(b->d_history);
     cudaFree(b->d_phase);
-    cudaFree(b->d_work);
     cudaFree(b->d_in);
     cudaFree(b->d_out);
     cudaFree(b->d_out16);

@@ -78,6 +78,8 @@ def _load():
     lib.sdrm_gfsk_mod_batch_sync.argtypes = [vp]
     lib.sdrm_gfsk_mod_batch_stream.restype = vp
     lib.sdrm_gfsk_mod_batch_stream.argtypes = [vp]
+    lib.sdrm_gfsk_mod_batch_input_stream.restype = vp
+    lib.sdrm_gfsk_mod_batch_input_stream.argtypes = [vp]
     lib.sdrm_gfsk_mod_batch_launch_count.restype = C.c_uint64
     lib.sdrm_gfsk_mod_batch_launch_count.argtypes = [vp]
     lib.sdrm_gfsk_mod_batch_destroy.argtypes = [vp]
@@ -505,7 +507,13 @@ class GfskModBatch:
 
     @property
     def stream(self):
+        """results are complete on this stream"""
         return lib.sdrm_gfsk_mod_batch_stream(self.handle)
+
+    @property
+    def input_stream(self):
+        """inputs are consumed on this stream"""
+        return lib.sdrm_gfsk_mod_batch_input_stream(self.handle)
 
     @property
     def launch_count(self):
