@@ -148,6 +148,24 @@ def cpu_reference_run(shape, seconds, n_threads=None):
             "seconds": sec, "symbols": int(symbols)}
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The driver parses stdout for ONE JSON line. Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for everything except emit_line()."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+
+
 def run_reference_arm(args, shape):
     """bench.py --impl reference: the reference's own CPU chain (oracle/_ref, built from the reference sources in place) on all
     host cores, same metric and workload shape; a step is a bounded sample (a few passes of 16 x 2 chunks), so that
@@ -158,7 +176,7 @@ def run_reference_arm(args, shape):
     from oracle import ref
     import workloads
     if not ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsdrmodem_ref.so not built"}))
+        emit_line({"impl": "reference", "unavailable": "oracle/_ref/libsdrmodem_ref.so not built"})
         return
     cores = os.cpu_count() or 1
     n = shape.chunk * 2
@@ -183,11 +201,12 @@ def run_reference_arm(args, shape):
                                    "bounded sample)" % (cores, shape.name), "channels": cores, "chunk": shape.chunk},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     import workloads
     shape = workloads.DemodShape("gmsk9600@192k/chunk%d" % args.chunk, 192000, 9600, 5000, 2, 2000, True, args.chunk)
     if args.impl == "reference":
@@ -205,6 +224,9 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    # host threads and the pinned buffers they allocate stay on the socket of this rank's GPU
+    all_cpus = os.sched_getaffinity(0)
+    local_cpus = sdrm.bind_thread_near_device(local_rank)
 
     n_ch, chunk = args.channels, args.chunk
     first_channel = rank * n_ch  # channel c of the job is the same signal on any sharding
@@ -365,6 +387,7 @@ def main():
     }
     cpu = None
     if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
+        os.sched_setaffinity(0, all_cpus)  # the reference gets every host core, not only the GPU's socket
         cpu = cpu_reference_run(shape, args.cpu_seconds)
         if cpu is not None:
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -377,11 +400,12 @@ def main():
                    "channels_per_gpu": n_ch, "chunk": chunk, "mode": args.mode, "parallelism": "channels sharded, no collective",
                    "l2": "inputs larger than L2 (2 x %.2f GiB rotating)" % (n_ch * chunk * 8 / 2 ** 30),
                    "realtime_channels_per_gpu": value / world * 1e6 / shape.sampling_freq,
-                   "flop_per_sample": flops_per_sample, "t1": t1, "t2": t2, "input_gen_s": gen_s},
+                   "flop_per_sample": flops_per_sample, "t1": t1, "t2": t2, "input_gen_s": gen_s,
+                   "host_cpus_near_gpu": local_cpus},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "error_flags": flags, "lib": sdrm.version(),
     }
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -224,6 +224,16 @@ int sdrm_samples_cf32_to_i16_device(const void *d_input, size_t in_stride, void 
 void *sdrm_pinned_alloc(size_t bytes);
 void sdrm_pinned_free(void *p);
 
+/*
+ * Moves the calling thread onto the CPUs that are local to CUDA device `device` (sysfs local_cpulist of its PCI function,
+ * intersected with the CPUs the process may use), so that pinned memory it allocates next lands on the device's socket.
+ * Returns the number of CPUs in the new mask, 0 when nothing was changed (no topology information, or no local CPU
+ * allowed), a negative errno on failure. Call it before sdrm_pinned_alloc / *_batch_create in a thread that feeds one GPU.
+ */
+int sdrm_bind_thread_near_device(int device);
+/* Parser behind it, exported for tests: number of CPUs in a sysfs cpu list such as "0-23,48-71", -1 if malformed. */
+int sdrm_cpulist_parse_count(const char *text);
+
 /* Library/runtime identification: "sdr-modem_b200 <version>; sm_100a; CUDA runtime <n>". */
 const char *sdrm_version(void);
 

@@ -41,6 +41,8 @@ def _load():
     lib.sdrm_pinned_alloc.restype = vp
     lib.sdrm_pinned_alloc.argtypes = [sz]
     lib.sdrm_pinned_free.argtypes = [vp]
+    lib.sdrm_bind_thread_near_device.argtypes = [i32]
+    lib.sdrm_cpulist_parse_count.argtypes = [C.c_char_p]
     lib.sdrm_fsk_demod_batch_create.argtypes = [C.POINTER(FskDemodBatchConfig), C.POINTER(vp)]
     lib.sdrm_fsk_demod_batch_process.argtypes = [vp, vp, sz, sz, vp, vp, sz, vp]
     lib.sdrm_fsk_demod_batch_submit.argtypes = [vp, vp, sz, sz]
@@ -127,6 +129,15 @@ class SdrmError(RuntimeError):
 def _check(code, what):
     if code != 0:
         raise SdrmError("%s failed with %d" % (what, code))
+
+
+def bind_thread_near_device(device):
+    """Move the calling thread onto the CPUs local to CUDA device `device`, so that pinned buffers allocated next are on its
+    socket. Returns the size of the new CPU mask, 0 if nothing changed."""
+    n = lib.sdrm_bind_thread_near_device(int(device))
+    if n < 0:
+        raise SdrmError("sdrm_bind_thread_near_device(%d) failed with %d" % (device, n))
+    return n
 
 
 class PinnedArray:

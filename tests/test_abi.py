@@ -87,3 +87,21 @@ def test_host_fast_atan2f_matches_oracle(sdrm, port):
     x = np.concatenate([rng.standard_normal(2000), [0, 1, 0, 0, 1.0, 1]]).astype(np.float32)
     got = np.array([lib.fast_atan2f(float(a), float(b)) for a, b in zip(y, x)], dtype=np.float32)
     assert np.array_equal(got.view(np.uint32), port.fast_atan2f(y, x).view(np.uint32))
+
+
+def test_cpulist_parser(sdrm):
+    """sysfs cpu lists behind sdrm_bind_thread_near_device (host/affinity.c)."""
+    count = sdrm.lib.sdrm_cpulist_parse_count
+    assert count(b"0-23\n") == 24
+    assert count(b"0-23,48-71\n") == 48
+    assert count(b"5") == 1
+    assert count(b"") == 0
+    assert count(b"3-1") == -1
+    assert count(b"x") == -1
+
+
+def test_bind_thread_without_gpu_is_an_error_not_a_crash(sdrm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    assert sdrm.lib.sdrm_bind_thread_near_device(0) < 0
