@@ -287,6 +287,9 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? 3 : 2) fir_tile_kernel(cons
     }
     const float2 one = p.one;
     const float2 negzero = p.negzero;
+    // The last tile of a row is usually ragged (131072 outputs are 51.2 tiles): warps whose outputs all lie beyond the end of
+    // the row skip the arithmetic (they still take part in the barriers) instead of filtering samples nobody stores.
+    const bool warp_has_outputs = m0 + (long long) (tid & ~31) * kR < p.n_out;
 
     for (int b = 0; b < n_blocks; b++) {
         const int st = (p.n_stages > 1) ? (b & 1) : 0;
@@ -295,10 +298,12 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? 3 : 2) fir_tile_kernel(cons
         const float2 *smp = smem_f2 + st * stage_f2;
         const float2 *tps = smp + p.stage_samples;
         const float2 *s = smp + odd + tid * (kR * D);
-        if (D == 1) {
-            fir_d1_block<FAST, ALIGNED>(acc, s, tps, nt, one, negzero);
-        } else {
-            fir_d2_block<FAST, ALIGNED>(acc, s, tps, nt, one, negzero);
+        if (warp_has_outputs) {
+            if (D == 1) {
+                fir_d1_block<FAST, ALIGNED>(acc, s, tps, nt, one, negzero);
+            } else {
+                fir_d2_block<FAST, ALIGNED>(acc, s, tps, nt, one, negzero);
+            }
         }
         if (b + p.n_stages < n_blocks) {
             __syncthreads();  // everyone is done reading this stage before TMA overwrites it
