@@ -61,6 +61,34 @@ __device__ __forceinline__ float step_spec2(float q, float d, float *out_p) {
     return lo ? au : (hi ? at : aq);
 }
 
+// predicated add: the offset -copysign(2pi, q) is one LOP3 on q, the comparison one FSETP beside it, and the wrap itself a
+// predicated FADD into q's own register: FADD -> (LOP3 | FSETP) -> @P FADD
+__device__ __forceinline__ float step_predadd(float p, float d) {
+    float q = __fadd_rn(p, d);
+    const float off = __uint_as_float((__float_as_uint(q) & 0x80000000u) ^ 0xC0C90FDBu);
+    if (fabsf(q) > kTwoPi) {
+        q = __fadd_rn(q, off);
+    }
+    return q;
+}
+
+// the same with the predication spelled out
+__device__ __forceinline__ float step_predadd_ptx(float p, float d) {
+    float q;
+    asm("{\n"
+        ".reg .pred w;\n"
+        ".reg .b32 off, aq;\n"
+        "add.rn.f32 %0, %1, %2;\n"
+        "lop3.b32 off, %0, 0x80000000, 0xC0C90FDB, 0x6a;\n"  // (a & b) ^ c
+        "abs.f32 aq, %0;\n"
+        "setp.gt.f32 w, aq, 0f40C90FDB;\n"
+        "@w add.rn.f32 %0, %0, off;\n"
+        "}\n"
+        : "=&f"(q)
+        : "f"(p), "f"(d));
+    return q;
+}
+
 template <int V>
 __global__ void chain(const float *d_in, float *out, long long *cycles) {
     __shared__ float d[N][32];
@@ -71,7 +99,7 @@ __global__ void chain(const float *d_in, float *out, long long *cycles) {
     float p = 0.0f;
     long long t0 = clock64();
     float *col = &d[0][threadIdx.x];
-    if (V >= 4) {
+    if (V >= 4 && V < 6) {
         p = col[0];  // pre-wrap state: q_0 = 0 + d_0
     }
     for (int pass = 0; pass < PASSES; pass++) {
@@ -79,7 +107,11 @@ __global__ void chain(const float *d_in, float *out, long long *cycles) {
             float *c = col + i0 * 32;
 #pragma unroll
             for (int i = 0; i < 32; i++) {
-                if (V < 4) {
+                if (V >= 6) {
+                    const float x = c[i * 32];
+                    p = V == 6 ? step_predadd(p, x) : step_predadd_ptx(p, x);
+                    c[i * 32] = p;
+                } else if (V < 4) {
                     const float x = c[i * 32];
                     p = V == 0 ? step_pred(p, x) : V == 1 ? step_mask(p, x) : V == 2 ? step_plain(p, x) : step_onepred(p, x);
                     c[i * 32] = p;
@@ -115,8 +147,8 @@ int main() {
     cudaMalloc(&cyc, 8);
     cudaMemcpy(d_in, h, N * 32 * 4, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 0);
-    float res[6][32];
-    long long c[6];
+    float res[8][32];
+    long long c[8];
     for (int rep = 0; rep < 2; rep++) {
         chain<0><<<1, 32>>>(d_in, out, cyc);
         cudaMemcpy(&c[0], cyc, 8, cudaMemcpyDeviceToHost);
@@ -136,6 +168,12 @@ int main() {
         chain<5><<<1, 32>>>(d_in, out, cyc);
         cudaMemcpy(&c[5], cyc, 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(res[5], out, 128, cudaMemcpyDeviceToHost);
+        chain<6><<<1, 32>>>(d_in, out, cyc);
+        cudaMemcpy(&c[6], cyc, 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(res[6], out, 128, cudaMemcpyDeviceToHost);
+        chain<7><<<1, 32>>>(d_in, out, cyc);
+        cudaMemcpy(&c[7], cyc, 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(res[7], out, 128, cudaMemcpyDeviceToHost);
     }
     cudaError_t e = cudaDeviceSynchronize();
     int same1 = 1, same3 = 1;
@@ -143,6 +181,13 @@ int main() {
         same1 &= res[0][i] == res[1][i];
         same3 &= res[0][i] == res[3][i];
     }
+    int same6 = 1, same7 = 1;
+    for (int i = 0; i < 32; i++) {
+        same6 &= res[0][i] == res[6][i];
+        same7 &= res[0][i] == res[7][i];
+    }
+    printf("predadd %.2f (same=%d)  predadd_ptx %.2f (same=%d) cycles/step\n", c[6] / (double) (N * PASSES), same6,
+           c[7] / (double) (N * PASSES), same7);
     printf("spec1 %.2f spec2 %.2f cycles/step (state differs by design; res %g %g %g)\n", c[4] / (double) (N * PASSES),
            c[5] / (double) (N * PASSES), res[0][0], res[4][0], res[5][0]);
     printf("err=%d pred %.2f  mask %.2f (same=%d)  plain %.2f  onepred %.2f (same=%d) cycles/step\n", (int) e, c[0] / (double) (N * PASSES),
