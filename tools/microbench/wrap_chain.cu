@@ -89,6 +89,17 @@ __device__ __forceinline__ float step_predadd_ptx(float p, float d) {
     return q;
 }
 
+// no predicate at all: u = 2pi - |q| is negative exactly when the phase wraps, and then |u| = |q| - 2pi < |q|. Flipping u's sign bit
+// (+ 0x80000000) makes every non-wrapping u, including +0 for |q| == 2pi, an unsigned number above any |q|, so one
+// add-and-unsigned-min picks the magnitude: FADD -> FADD -> VIADDMNMX -> LOP3
+__device__ __forceinline__ float step_viaddmin(float p, float d) {
+    const float q = __fadd_rn(p, d);
+    const float u = __fsub_rn(kTwoPi, fabsf(q));
+    const uint32_t qb = __float_as_uint(q);
+    const uint32_t mag = __viaddmin_u32(__float_as_uint(u), 0x80000000u, qb & 0x7fffffffu);
+    return __uint_as_float(mag | (qb & 0x80000000u));
+}
+
 template <int V>
 __global__ void chain(const float *d_in, float *out, long long *cycles) {
     __shared__ float d[N][32];
@@ -109,7 +120,7 @@ __global__ void chain(const float *d_in, float *out, long long *cycles) {
             for (int i = 0; i < 32; i++) {
                 if (V >= 6) {
                     const float x = c[i * 32];
-                    p = V == 6 ? step_predadd(p, x) : step_predadd_ptx(p, x);
+                    p = V == 6 ? step_predadd(p, x) : V == 7 ? step_predadd_ptx(p, x) : step_viaddmin(p, x);
                     c[i * 32] = p;
                 } else if (V < 4) {
                     const float x = c[i * 32];
@@ -147,8 +158,8 @@ int main() {
     cudaMalloc(&cyc, 8);
     cudaMemcpy(d_in, h, N * 32 * 4, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 0);
-    float res[8][32];
-    long long c[8];
+    float res[9][32];
+    long long c[9];
     for (int rep = 0; rep < 2; rep++) {
         chain<0><<<1, 32>>>(d_in, out, cyc);
         cudaMemcpy(&c[0], cyc, 8, cudaMemcpyDeviceToHost);
@@ -174,6 +185,9 @@ int main() {
         chain<7><<<1, 32>>>(d_in, out, cyc);
         cudaMemcpy(&c[7], cyc, 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(res[7], out, 128, cudaMemcpyDeviceToHost);
+        chain<8><<<1, 32>>>(d_in, out, cyc);
+        cudaMemcpy(&c[8], cyc, 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(res[8], out, 128, cudaMemcpyDeviceToHost);
     }
     cudaError_t e = cudaDeviceSynchronize();
     int same1 = 1, same3 = 1;
@@ -186,6 +200,11 @@ int main() {
         same6 &= res[0][i] == res[6][i];
         same7 &= res[0][i] == res[7][i];
     }
+    int same8 = 1;
+    for (int i = 0; i < 32; i++) {
+        same8 &= res[0][i] == res[8][i];
+    }
+    printf("viaddmin %.2f (same=%d) cycles/step\n", c[8] / (double) (N * PASSES), same8);
     printf("predadd %.2f (same=%d)  predadd_ptx %.2f (same=%d) cycles/step\n", c[6] / (double) (N * PASSES), same6,
            c[7] / (double) (N * PASSES), same7);
     printf("spec1 %.2f spec2 %.2f cycles/step (state differs by design; res %g %g %g)\n", c[4] / (double) (N * PASSES),
