@@ -34,3 +34,18 @@ for label, use_dc, flags in (("dc on", True, 0), ("dc off", False, 0), ("no tail
     torch.cuda.synchronize()
     print(label, "ms per call %.3f" % (start.elapsed_time(end) / steps))
     b.close()
+
+# K1 / K3 of a call whose filters run beside the previous call's tail, against the same kernels alone
+b = sdrm.FskDemodBatch(n_ch, 192000, 9600, 5000, 2, 2000, True, chunk, max_symbols_per_call=int(chunk / 20 * 1.2) + 64)
+b.set_profiling(True)
+for k in range(3):
+    b.process_device(bufs[k % 2].data_ptr(), chunk, chunk)
+    b.release()
+    alone = b.stage_times()
+for k in range(6):
+    b.process_device(bufs[k % 2].data_ptr(), chunk, chunk)
+    b.release()
+beside = b.stage_times()
+print("alone   K1 %.3f K3+hist %.3f tail %.3f" % (alone[0], alone[1], alone[2]))
+print("beside  K1 %.3f K3+hist %.3f tail %.3f" % (beside[0], beside[1], beside[2]))
+b.close()
