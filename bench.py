@@ -41,6 +41,7 @@ def parse_args():
     p.add_argument("--mode", default="exact", choices=["exact", "fast"])
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-fma-line", action="store_true", help="skip the extra measurement in the FMA arithmetic mode")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--debug-no-tail", action="store_true", help="measurement aid: skip the serial tail (invalid result)")
     return p.parse_args()
@@ -292,6 +293,38 @@ def main():
     samples_per_step = world * n_ch * chunk
     value = samples_per_step * args.steps / (ms_total * 1e-3) / 1e6
 
+    # ---- the same workload in the optional FMA arithmetic (one FFMA2 per tap, not the parity-defining mode): shows what the
+    # kernels reach once the bit-exact multiply-then-add no longer halves the pipe's useful rate -------------------------------
+    fma_mode = None
+    if args.mode == "exact" and world == 1 and not args.no_fma_line:
+        fast = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=cap, fast=True, device=local_rank)
+        fast_fir = torch.cuda.ExternalStream(fast.stream, device=device)
+        fast_tail = torch.cuda.ExternalStream(fast.tail_stream, device=device)
+        fast_steps = max(3, min(args.steps, 20))
+        for k in range(max(3, args.warmup)):
+            fast.process_device(bufs[k % n_buf].data_ptr(), chunk, chunk)
+            fast.release()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(fast_fir)
+        for k in range(fast_steps):
+            fast.process_device(bufs[k % n_buf].data_ptr(), chunk, chunk)
+            fast.release()
+        f1.record(fast_tail)
+        torch.cuda.synchronize()
+        fast_ms = f0.elapsed_time(f1) / fast_steps
+        fast.set_profiling(True)
+        fast_k1 = []
+        for k in range(3):
+            fast.process_device(bufs[k % n_buf].data_ptr(), chunk, chunk)
+            fast.release()
+            fast_k1.append(fast.stage_times()[0])
+        fma_mode = {"value": n_ch * chunk / (fast_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": fast_ms, "steps": fast_steps,
+                    "kernel_ms": float(np.mean(fast_k1)), "error_flags": fast.error_flags(),
+                    "note": "SDRM_FLAG_FAST_FMA: same summation order, fused rounding; bit-identical to the FMA-order build of the "
+                            "reference, not to its strict build"}
+        fast.close()
+
     # ---- end to end through the host-buffer entry points (pinned input, H2D + D2H in the timed region) ----------
     e2e = None
     if not args.no_e2e:
@@ -382,6 +415,9 @@ def main():
         "kernel_ms": k1, "kernel_share_of_step": k1 / (ms_total / args.steps),
         "traffic": k1_traffic(n_ch * chunk),
         "hbm": {"achieved": (in_bytes + in_bytes / 2) / (k1 * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s"},
+        "fma_mode": None if fma_mode is None else dict(
+            fma_mode, achieved=k1_flops / (fma_mode["kernel_ms"] * 1e-3) / 1e12,
+            frac=k1_flops / (fma_mode["kernel_ms"] * 1e-3) / 1e12 / fp32_peak_tflops),
         "stage_ms": {"lpf1_quad": k1, "lpf2": float(np.mean(k3_ms)), "dc_clock_tail": float(np.mean(tail_ms)),
                      "call_unpipelined": float(np.mean(call_ms))},
     }
