@@ -230,61 +230,71 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// Tile geometry of the walker, chosen by the launcher from the number of channel groups (= CTAs). Every tile costs its warp
+// ~450 cycles of barrier wait, proxy fence and copy issue in series with the recurrence, so tiles should be as long as shared
+// memory allows: 512 steps per tile (3 tiles, 192 KB) while there is at most one CTA per SM, shorter tiles when several
+// CTAs have to share an SM to stay in one wave. C4 (1024 channels x 32768 steps): 0.49 ms per call with 128-step tiles,
+// 0.40 with 256, 0.385 with 512; the recurrence alone is 0.34 ms.
+template <int ROWS, int STAGES, int PREFETCH>
+struct WalkCfg {
+    static constexpr int kRows = ROWS;                   // time steps per tile
+    static constexpr int kTile = ROWS * 32;              // floats per tile
+    static constexpr int kStages = STAGES;               // tiles in the ring
+    static constexpr int kPrefetch = PREFETCH;           // loads run this many tiles ahead; a stage is reloaded
+                                                         // kStages - kPrefetch tiles after its store
+    static constexpr int kSmem = STAGES * ROWS * 32 * 4 + STAGES * 8;
+};
+
 // The serial pass: phase = wrap(phase + increment[m]), one warp per group of 32 channels, lane = channel.
-// The increments stream in as 4 KB tiles (32 time steps x 32 channels, contiguous in the GTC layout) through a ring of
+// The increments stream in as tiles of Cfg::kRows time steps x 32 channels (contiguous in the GTC layout) through a ring of
 // kStages TMA bulk copies, the phases go back the same way in place, so that the recurrence itself — one dependent add
 // and select per sample — is all the warp waits for.
-constexpr int kWalkRows = 128;            // time steps per walker tile: 16 KB per bulk copy amortises the per-tile
-constexpr int kWalkTile = kWalkRows * 32;  // barrier / fence / issue overhead (~450 cycles) over 128 serial steps
-constexpr int kStages = 6;                // tiles in the ring (96 KB of dynamic shared memory)
-constexpr int kPrefetch = 3;  // loads run this many tiles ahead; a stage is reloaded kStages - kPrefetch tiles after its store
-constexpr int kWalkSmem = kStages * kWalkTile * 4 + kStages * 8;
-
+template <class Cfg>
 __global__ void __launch_bounds__(32) phase_walk_kernel(float *work, size_t rows, float *phase_state, long long n, int n_ch) {
     extern __shared__ __align__(128) unsigned char walk_smem[];
-    float(*tiles)[kWalkTile] = reinterpret_cast<float(*)[kWalkTile]>(walk_smem);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(walk_smem + kStages * kWalkTile * 4);
+    float(*tiles)[Cfg::kTile] = reinterpret_cast<float(*)[Cfg::kTile]>(walk_smem);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(walk_smem + Cfg::kStages * Cfg::kTile * 4);
     const int lane = threadIdx.x;
     const int group = blockIdx.x;
     const int ch = group * 32 + lane;
     float *base = work + (size_t) group * rows * 32;
-    const long long n_tiles = (n + kWalkRows - 1) / kWalkRows;
+    const long long n_tiles = (n + Cfg::kRows - 1) / Cfg::kRows;
     if (lane == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < Cfg::kStages; s++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     auto fetch = [&](long long t) {
-        const int s = (int) (t % kStages);
-        const int nr = (int) min((long long) kWalkRows, n - t * kWalkRows);
+        const int s = (int) (t % Cfg::kStages);
+        const int nr = (int) min((long long) Cfg::kRows, n - t * Cfg::kRows);
         const uint32_t bytes = (uint32_t) nr * 128u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(tiles[s])),
-                     "l"(base + (size_t) t * kWalkTile), "r"(bytes), "r"(smem_u32(&bars[s]))
+                     "l"(base + (size_t) t * Cfg::kTile), "r"(bytes), "r"(smem_u32(&bars[s]))
                      : "memory");
     };
     if (lane == 0) {
-        for (long long t = 0; t < kPrefetch && t < n_tiles; t++) {
+        for (long long t = 0; t < Cfg::kPrefetch && t < n_tiles; t++) {
             fetch(t);
         }
     }
     float p = ch < n_ch ? phase_state[ch] : 0.0f;
     for (long long t = 0; t < n_tiles; t++) {
-        const int s = (int) (t % kStages);
-        if (lane == 0 && t + kPrefetch < n_tiles) {
+        const int s = (int) (t % Cfg::kStages);
+        if (lane == 0 && t + Cfg::kPrefetch < n_tiles) {
             // the stage being refilled was stored kStages - kPrefetch tiles ago: all but the newest
             // kStages - kPrefetch - 1 bulk stores must have finished reading shared memory
-            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStages - kPrefetch - 1) : "memory");
-            fetch(t + kPrefetch);
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(Cfg::kStages - Cfg::kPrefetch - 1) : "memory");
+            fetch(t + Cfg::kPrefetch);
         }
         __syncwarp();
-        mbar_wait(&bars[s], (uint32_t) ((t / kStages) & 1));
+        mbar_wait(&bars[s], (uint32_t) ((t / Cfg::kStages) & 1));
         float *tile = tiles[s] + lane;
-        const int nr = (int) min((long long) kWalkRows, n - t * kWalkRows);
-        if (nr == kWalkRows) {
-            for (int r0 = 0; r0 < kWalkRows; r0 += 32) {
+        const int nr = (int) min((long long) Cfg::kRows, n - t * Cfg::kRows);
+        if (nr == Cfg::kRows) {
+            for (int r0 = 0; r0 < Cfg::kRows; r0 += 32) {
 #pragma unroll
                 for (int r = 0; r < 32; r++) {
                     p = wrap_step(p, tile[(r0 + r) * 32]);
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(32) phase_walk_kernel(float *work, size_t rows
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + (size_t) t * kWalkTile),
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + (size_t) t * Cfg::kTile),
                          "r"(smem_u32(tiles[s])), "r"((uint32_t) nr * 128u)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -425,12 +435,34 @@ extern "C" int sdrm_cu_phase_walk(float *work, size_t rows, float *phase_state, 
     if ((long long) rows < n || ((uintptr_t) work & 127) != 0) {
         return -22;
     }
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(phase_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem);
-        configured = true;
+    const int groups = (n_ch + 31) / 32;
+    int device = 0, n_sms = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        n_sms = 1;
     }
-    phase_walk_kernel<<<(n_ch + 31) / 32, 32, kWalkSmem, (cudaStream_t) stream_ptr>>>(work, rows, phase_state, n, n_ch);
+    cudaStream_t stream = (cudaStream_t) stream_ptr;
+    if (2 * groups <= n_sms) {
+        // 192 KB per CTA: only while at least half of the SMs stay free for the shaping and trigonometry passes of the
+        // neighbouring calls, which overlap this one (4096 channels with 512-step tiles: 1.11 ms per call against 0.91)
+        using Cfg = WalkCfg<512, 3, 1>;
+        // ... and the walker asks for all the shared memory of its SM, so that no CTA of those passes lands beside it and takes
+        // issue slots from its single warp (C4: 0.383 -> 0.368 ms per call)
+        int smem = Cfg::kSmem;
+        int most = 0;
+        if (cudaDeviceGetAttribute(&most, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess && most > smem) {
+            smem = most;
+        }
+        cudaFuncSetAttribute(phase_walk_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        phase_walk_kernel<Cfg><<<groups, 32, smem, stream>>>(work, rows, phase_state, n, n_ch);
+    } else if (groups <= 2 * n_sms) {
+        using Cfg = WalkCfg<256, 3, 1>;  // 96 KB: two CTAs per SM
+        cudaFuncSetAttribute(phase_walk_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        phase_walk_kernel<Cfg><<<groups, 32, Cfg::kSmem, stream>>>(work, rows, phase_state, n, n_ch);
+    } else {
+        using Cfg = WalkCfg<128, 3, 1>;  // 48 KB: four CTAs per SM, one walker per scheduler
+        cudaFuncSetAttribute(phase_walk_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        phase_walk_kernel<Cfg><<<groups, 32, Cfg::kSmem, stream>>>(work, rows, phase_state, n, n_ch);
+    }
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }
