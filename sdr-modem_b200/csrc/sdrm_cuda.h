@@ -133,6 +133,7 @@ typedef struct {
     int n_rows;
     int n_ch;
     int dc_length;       /* 0: no dc blocker */
+    int div_steps;       /* sdrm_division_steps(dc_length): corrections the branch-free division needs (1 or 2); 0 = use __fdiv_rn */
     float *delay;        /* float [4][n_groups][dc_length][32] (last L inputs of each moving average), then
                             float [n_groups][dx_length][32] (group delay line); zero-initialised */
     int dx_length;       /* >= 2 * dc_length - 2 + 256: the pipeline's first stage writes ahead of its last */
@@ -161,7 +162,7 @@ int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream);
 
 /* Self test (synchronous): counts sums for which the tail's branch-free division by `length` differs from an IEEE
  * division, over blocks * 256 * per_thread pseudo-random values. Used by tests only. */
-int sdrm_cu_selftest_div(int length, uint32_t seed, int blocks, int per_thread, unsigned long long *mismatches);
+int sdrm_cu_selftest_div(int length, int steps, uint32_t seed, int blocks, int per_thread, unsigned long long *mismatches);
 
 /*
  * NCO / mixer (reference src/dsp/sig_source.c:43-75) over CF rows: out = in * amp * exp(j p), p advancing by

@@ -138,22 +138,51 @@ __device__ __forceinline__ float dot_step(bool fast, float acc, float v, float t
     return fast ? __fmaf_rn(v, t, acc) : __fadd_rn(acc, __fmul_rn(v, t));
 }
 
-// sum / L, correctly rounded, for a constant L with rcp = RN(1/L): two Markstein corrections of q0 = RN(sum * rcp).
-// Valid inside the exponent range where the residuals are exact (see outside_fast_division_range).
+// sum / L, correctly rounded, for a constant L with rcp = RN(1/L): Markstein corrections of q0 = RN(sum * rcp).
+// Valid inside the exponent range where the residuals are exact (see SumRange). One correction is enough for most
+// lengths, every length the reference's parameters produce among them, but not provably for all: the host checks the
+// length at create over all 2^23 mantissas (host/taps.c, sdrm_division_steps) and passes STEPS = 1 or 2.
 // A zero sum: +0 gives q0 = e0 = q1 = ... = +0. (-0 would come back as +0, but the running sums of this kernel are never -0:
 // they start at +0 and RN(x + (-x)) = +0; the per-block dc_blocker handle in tail.cu keeps an explicit test.)
+template <int STEPS>
 __device__ __forceinline__ float div_by_length(float sum, float length_f, float rcp) {
+    if (STEPS == 0) {
+        return __fdiv_rn(sum, length_f);
+    }
     const float q0 = __fmul_rn(sum, rcp);
     const float e0 = __fmaf_rn(-q0, length_f, sum);
     const float q1 = __fmaf_rn(e0, rcp, q0);
+    if (STEPS == 1) {
+        return q1;
+    }
     const float e1 = __fmaf_rn(-q1, length_f, sum);
     return __fmaf_rn(e1, rcp, q1);
 }
 
-// sums for which div_by_length is not proven (huge, non-finite, or tiny but non-zero): the caller uses __fdiv_rn
+// Sums for which div_by_length is not proven (huge, non-finite, or tiny but non-zero) make their block use __fdiv_rn.
+// The test runs over the 32 sums of a block as two unsigned reductions of the magnitude bits shifted left by one (the
+// sign falls off, order is preserved): the largest, and the smallest of (bits - 1), where the wrap-around sends a zero
+// sum — which the fast path divides correctly — to the far end. Three integer instructions per sum instead of three
+// comparisons and two predicate merges.
+struct SumRange {
+    uint32_t largest = 0u;
+    uint32_t smallest_m1 = 0xffffffffu;
+    __device__ __forceinline__ void add(float sum) {
+        const uint32_t u = __float_as_uint(sum) << 1;
+        largest = max(largest, u);
+        smallest_m1 = min(smallest_m1, u - 1u);
+    }
+    // 1.0e18f = 0x5D5E0B6B, 1.0e-18f = 0x219392EF
+    __device__ __forceinline__ bool outside() const {
+        return largest >= (0x5D5E0B6Bu << 1) || smallest_m1 < (0x219392EFu << 1) - 1u;
+    }
+};
+
+// the same test on one value (self test)
 __device__ __forceinline__ bool outside_fast_division_range(float sum) {
-    const float mag = fabsf(sum);
-    return !(mag < 1.0e18f) || (mag < 1.0e-18f && sum != 0.0f);
+    SumRange r;
+    r.add(sum);
+    return r.outside();
 }
 
 // Shared-memory map of one CTA.
@@ -249,7 +278,7 @@ __device__ __forceinline__ void ring_put(float *ring_lane, int pos, int ring_slo
 //   moving average  y = in - in[n-L] + y_prev ; out = y / L                           (dc_blocker.c:52-64)
 //   last stage      x[n-(2L-2)] - y4 appended to the clock's sample ring              (dc_blocker.c:110-114)
 // FULL blocks carry no per-row guards, so the 32 rows form one basic block that ptxas interleaves freely.
-template <int PROD, bool FULL>
+template <int PROD, bool FULL, int DIVSTEPS>
 __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Layout &s, const Arrays &g, int warp, int lane, int b,
                                                int nr, const Cursors &c, float &sum, float rcp) {
     const bool has_dc = PROD == 4;
@@ -320,14 +349,14 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
     // All 32 quotients as pure arithmetic, in place: 32 independent FMUL + 4 FFMA chains that ptxas interleaves. (With the
     // stores and the stage test inside this loop every row became its own basic block behind a branch, the chains ran one
     // after the other through the same two registers and a block took 5600 cycles instead of a few hundred.)
-    bool exact = false;
+    SumRange range;
 #pragma unroll
     for (int r = 0; r < kBlockRows; r++) {
         if (FULL || r < nr) {
-            exact |= outside_fast_division_range(y[r]);
+            range.add(y[r]);
         }
     }
-    if (__any_sync(0xffffffffu, exact)) {
+    if (DIVSTEPS == 0 || __any_sync(0xffffffffu, range.outside())) {
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
@@ -338,7 +367,7 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
-                y[r] = div_by_length(y[r], length_f, rcp);
+                y[r] = div_by_length<DIVSTEPS>(y[r], length_f, rcp);
             }
         }
     }
@@ -374,7 +403,7 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
 
 // PROD producer warps (4 moving averages, or 1 plain copier when the dc blocker is off) + 1 clock warp.
 // All per-channel arrays are padded to a multiple of 32 channels, so every lane owns real memory.
-template <int PROD>
+template <int PROD, int DIVSTEPS>
 __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_tail_args a) {
     extern __shared__ __align__(128) float smem[];
     Layout s;
@@ -467,9 +496,9 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                 }
                 mbar_wait(s.bars + warp * 2 + (b & 1), (uint32_t) ((b >> 1) & 1));
                 if (nr == kBlockRows) {
-                    producer_block<PROD, true>(a, s, arrays, warp, lane, b, nr, cur, sum, rcp);
+                    producer_block<PROD, true, DIVSTEPS>(a, s, arrays, warp, lane, b, nr, cur, sum, rcp);
                 } else {
-                    producer_block<PROD, false>(a, s, arrays, warp, lane, b, nr, cur, sum, rcp);
+                    producer_block<PROD, false, DIVSTEPS>(a, s, arrays, warp, lane, b, nr, cur, sum, rcp);
                 }
                 cur = nxt;
                 // this block's delay-line stores are done before the step ends: their source tile is recycled two steps
@@ -575,6 +604,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
 
 // Self test of div_by_length: compares the branch-free form with __fdiv_rn on pseudo-random sums (all exponents the
 // fast path accepts, both signs) and counts disagreements, including "redo" requests inside the accepted range.
+template <int STEPS>
 __global__ void div_selftest_kernel(int length, uint32_t seed, int per_thread, unsigned long long *mismatches) {
     const float length_f = (float) length;
     const float rcp = __frcp_rn(length_f);
@@ -589,7 +619,7 @@ __global__ void div_selftest_kernel(int length, uint32_t seed, int per_thread, u
         const uint32_t bits = (x & 0x807FFFFFu) | (expo << 23);
         const float sum = __uint_as_float(bits);
         const bool redo = outside_fast_division_range(sum);
-        const float fast = div_by_length(sum, length_f, rcp);
+        const float fast = div_by_length<STEPS>(sum, length_f, rcp);
         const float exact = __fdiv_rn(sum, length_f);
         if (redo || __float_as_uint(fast) != __float_as_uint(exact)) {
             bad++;
@@ -602,13 +632,20 @@ __global__ void div_selftest_kernel(int length, uint32_t seed, int per_thread, u
 
 }  // namespace
 
-extern "C" int sdrm_cu_selftest_div(int length, uint32_t seed, int blocks, int per_thread, unsigned long long *h_mismatches) {
+extern "C" int sdrm_cu_selftest_div(int length, int steps, uint32_t seed, int blocks, int per_thread,
+                                    unsigned long long *h_mismatches) {
     unsigned long long *d = nullptr;
     if (cudaMalloc(&d, sizeof(*d)) != cudaSuccess) {
         return -12;
     }
     cudaMemset(d, 0, sizeof(*d));
-    div_selftest_kernel<<<blocks, 256>>>(length, seed, per_thread, d);
+    if (steps == 1) {
+        div_selftest_kernel<1><<<blocks, 256>>>(length, seed, per_thread, d);
+    } else if (steps == 0) {
+        div_selftest_kernel<0><<<blocks, 256>>>(length, seed, per_thread, d);
+    } else {
+        div_selftest_kernel<2><<<blocks, 256>>>(length, seed, per_thread, d);
+    }
     cudaError_t err = cudaMemcpy(h_mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost);
     cudaFree(d);
     return err == cudaSuccess ? 0 : -(int) err - 1000;
@@ -631,7 +668,9 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
     const size_t floats = (size_t) kTapsFloats + (size_t) (args->ring_slots + kMirror) * 32 + (size_t) (prod - 1) * 2 * kTile + 2 * kTile +
                           (size_t) prod * 2 * kTile + 2 * kTile;
     const size_t smem = floats * sizeof(float) + (size_t) prod * 2 * sizeof(uint64_t);
-    void (*kernel)(const sdrm_tail_args) = has_dc ? demod_tail_kernel<4> : demod_tail_kernel<1>;
+    void (*kernel)(const sdrm_tail_args) =
+        !has_dc ? demod_tail_kernel<1, 2>
+                : (args->div_steps == 1 ? demod_tail_kernel<4, 1> : (args->div_steps == 2 ? demod_tail_kernel<4, 2> : demod_tail_kernel<4, 0>));
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess) {
         return -(int) err - 1000;

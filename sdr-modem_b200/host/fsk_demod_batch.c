@@ -68,6 +68,7 @@ struct sdrm_fsk_demod_batch_t {
 
     /* dc blocker */
     int dc_len;
+    int div_steps; /* sdrm_division_steps(dc_len) */
     int dx_len;
     float *d_delay;
     float *d_sums;
@@ -209,6 +210,7 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
             goto fail;
         }
         b->dx_len = 2 * b->dc_len - 2 + 256;
+        b->div_steps = sdrm_division_steps(b->dc_len);
         code = sdrm_dev_zalloc((void **) &b->d_delay, ((size_t) 4 * b->dc_len + b->dx_len) * b->n_ch_pad * sizeof(float));
         if (code != 0) goto fail;
         code = sdrm_dev_zalloc((void **) &b->d_sums, (size_t) 4 * b->n_ch_pad * sizeof(float));
@@ -399,6 +401,7 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     ca.n_rows = n_rows;
     ca.n_ch = (int) b->n_ch;
     ca.dc_length = b->dc_len;
+    ca.div_steps = b->div_steps;
     ca.delay = b->d_delay;
     ca.sums = b->d_sums;
     ca.delay_stride = b->n_ch_pad;

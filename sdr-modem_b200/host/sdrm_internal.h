@@ -57,6 +57,9 @@ int sdrm_convolve_full(const float *x, size_t x_len, const float *y, size_t y_le
 /* Uploads taps reversed and duplicated into float2 (h, h), padded with zeros to an even count + 2. */
 int sdrm_upload_taps_dup(const float *taps, size_t len, void **d_taps);
 
+/* Markstein corrections needed so that the tail's division by `length` is an IEEE division (exhaustive check, ~20 ms). */
+int sdrm_division_steps(int length);
+
 /* Device copies of the constant tables (tables_data.h). */
 int sdrm_upload_atan_table(float **d_table);
 int sdrm_upload_mmse_table(float **d_table);

@@ -9,6 +9,7 @@
  *                          (reference src/dsp/gfsk_mod.c:17-41)
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -142,6 +143,69 @@ int sdrm_upload_taps_dup(const float *taps, size_t len, void **d_taps) {
     }
     free(dup);
     return code;
+}
+
+/*
+ * How many Markstein corrections the tail kernel's division by `length` needs to round like an IEEE division:
+ * q0 = RN(a * rcp), e = fma(-q, L, a), q' = fma(e, rcp, q). Inside the exponent range the kernel accepts nothing
+ * underflows or overflows, so a and 2^k a behave alike and the 2^23 mantissas of one binade cover every operand (the
+ * arithmetic is symmetric in sign). One correction is enough for every length tried (all that 32 * samples-per-symbol
+ * gives for the reference's parameters); the check is what makes that a fact for the length at hand. Returns 1 or 2,
+ * or 0 if even two corrections fail (the kernel then keeps __fdiv_rn, never seen).
+ */
+static int division_steps_uncached(int length) {
+    const float L = (float) length;
+    const float rcp = 1.0f / L;
+    int one_ok = 1;
+    int two_ok = 1;
+    for (uint32_t m = 0; m < (1u << 23); m++) {
+        union {
+            uint32_t u;
+            float f;
+        } a;
+        a.u = 0x3f800000u | m;
+        const float exact = a.f / L;
+        const float q0 = a.f * rcp;
+        const float q1 = fmaf(fmaf(-q0, L, a.f), rcp, q0);
+        if (q1 != exact) {
+            one_ok = 0;
+            const float q2 = fmaf(fmaf(-q1, L, a.f), rcp, q1);
+            if (q2 != exact) {
+                two_ok = 0;
+                break;
+            }
+        }
+    }
+    return one_ok ? 1 : (two_ok ? 2 : 0);
+}
+
+int sdrm_division_steps(int length) {
+    /* the check takes tens of milliseconds; handles are created by the hundred (one per session), lengths are few */
+    static pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
+    static int known_length[16];
+    static int known_steps[16];
+    static int known = 0;
+    if (length <= 0) {
+        return 0;
+    }
+    pthread_mutex_lock(&lock);
+    for (int i = 0; i < known; i++) {
+        if (known_length[i] == length) {
+            const int steps = known_steps[i];
+            pthread_mutex_unlock(&lock);
+            return steps;
+        }
+    }
+    pthread_mutex_unlock(&lock);
+    const int steps = division_steps_uncached(length);
+    pthread_mutex_lock(&lock);
+    if (known < 16) {
+        known_length[known] = length;
+        known_steps[known] = steps;
+        known++;
+    }
+    pthread_mutex_unlock(&lock);
+    return steps;
 }
 
 const float *sdrm_host_atan_table(void) { return (const float *) sdrm_atan_bits; }

@@ -105,3 +105,11 @@ def test_bind_thread_without_gpu_is_an_error_not_a_crash(sdrm):
     if torch.cuda.is_available():
         pytest.skip("needs a box without a GPU")
     assert sdrm.lib.sdrm_bind_thread_near_device(0) < 0
+
+
+def test_division_steps_check_runs_on_the_host(sdrm):
+    """host/taps.c: exhaustive proof, per dc-blocker length, of how many corrections the tail's branch-free division needs."""
+    steps = sdrm.lib.sdrm_division_steps
+    for length in (320, 160, 107, 32, 3, 33333):
+        assert steps(length) == 1
+    assert steps(0) == 0

@@ -227,12 +227,15 @@ def test_dropin_create_errors(sdrm):
         sdrm.FskDemod(0, 4800, 5000, 2, 2000, True, 4096)
 
 
+@pytest.mark.parametrize("steps", [1, 2, 0])
 @pytest.mark.parametrize("length", [320, 160, 32, 3200, 17, 1000, 4096, 33333])
-def test_tail_division_by_length_is_ieee(sdrm, length):
+def test_tail_division_by_length_is_ieee(sdrm, length, steps):
     """The fused tail divides running sums by the dc blocker length without a generic division; it must round like one
-    (reference src/dsp/dc_blocker.c:63 is a true float division)."""
+    (reference src/dsp/dc_blocker.c:63 is a true float division). steps = Markstein corrections (the host proves per
+    length, over all 2^23 mantissas, that one is enough before the kernel is allowed to use one); 0 = __fdiv_rn."""
     lib = sdrm.lib
-    lib.sdrm_cu_selftest_div.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
+    lib.sdrm_cu_selftest_div.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
+    assert lib.sdrm_division_steps(length) == 1
     bad = C.c_ulonglong(123)
-    assert lib.sdrm_cu_selftest_div(length, 12345 + length, 1184, 4096, C.byref(bad)) == 0
+    assert lib.sdrm_cu_selftest_div(length, steps, 12345 + length, 1184, 4096, C.byref(bad)) == 0
     assert bad.value == 0
