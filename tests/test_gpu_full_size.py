@@ -123,3 +123,35 @@ def test_modulator_to_demodulator_round_trip_full_size(sdrm):
         lags.add(best[1])
     assert worst <= 64 and total <= 200, "bit errors after settling: worst channel %d, all channels %d" % (worst, total)
     assert max(lags) - min(lags) <= 1, sorted(lags)
+
+
+def test_c3_literal_chain_subset(sdrm, port, ref):
+    """BASELINE configs[2], the literal dsp_worker chain: doppler_process_rx -> fsk_demod_create(2400000, 2400, 5000, 100,
+    2000, true, 131072), i.e. a 9325-tap lpf1 (18 tap blocks) and a 2891-tap lpf2 decimating by 100, in 131072-sample calls.
+    The oracle manages 0.15 Msamples/s at this shape, so three channels with their own Doppler clocks and two calls each are
+    checked (SURVEY.md section 8d). The Doppler stage is compared with the reference build inside its trigonometric tolerance;
+    the demodulator is then bit-compared on exactly the samples the GPU Doppler stage produced."""
+    from conftest import LUCKY7_TLE
+    fs, baud, chunk, calls, n_ch = 2400000, 2400, 131072, 2, 3
+    shape = workloads.DemodShape("gmsk2400@2.4M", fs, baud, 5000, 100, 2000, True, chunk)
+    iq = workloads.gfsk_channels(n_ch, calls * chunk, shape, seed=31, max_offset_hz=4000.0).numpy()
+    lat, lon = float(np.float32(53.72)), float(np.float32(47.57))
+    starts = [1583840449 + 37 * c for c in range(n_ch)]
+    dop = sdrm.DopplerBatch([sdrm.doppler_channel(lat, lon, 0.0, 0, starts[c], LUCKY7_TLE) for c in range(n_ch)], fs, 437525000,
+                            chunk)
+    corrected = np.concatenate([dop.process(iq[:, k * chunk:(k + 1) * chunk]) for k in range(calls)], axis=1)
+    dop.close()
+    for c in range(n_ch):
+        want = ref.doppler(lat, lon, 0.0, fs, 437525000, 0, starts[c], chunk, LUCKY7_TLE).run(iq[c], chunk)
+        same = corrected[c].view(np.uint32) == want.view(np.uint32)
+        assert same.mean() > 0.99999 and np.abs(corrected[c] - want).max() < 1e-6, "doppler channel %d" % c
+    batch = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, soft=True)
+    try:
+        hard, soft = batch.run_stream(corrected, chunk)
+        assert batch.error_flags() == 0
+    finally:
+        batch.close()
+    for c in range(n_ch):
+        want_hard, want_soft = port.FskDemod(*shape.create_args, chunk).run(corrected[c], chunk)
+        assert len(want_hard) > calls * chunk // 1000 - 80
+        assert same_bits(hard[c], want_hard) and same_bits(soft[c], want_soft), "demod channel %d" % c
