@@ -54,6 +54,7 @@ typedef struct {
     long long tc_head;       /* TC only: absolute row of output 0 */
     float qd_gain;           /* QD_PAIR only */
     const float *atan_table; /* QD_PAIR only: 257 floats on the device */
+    const void *h_taps_dup;  /* optional HOST copy of taps_dup (n_taps float2): short filters pass their taps as kernel parameters */
 } sdrm_fir_args;
 
 int sdrm_cu_fir(const sdrm_fir_args *args, void *stream);

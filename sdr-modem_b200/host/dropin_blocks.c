@@ -75,6 +75,7 @@ struct fir_core {
     int phase;
     int cur;
     void *d_taps;
+    float *h_taps; /* host copy of the (h, h) pairs */
     void *d_hist[2];
     void *d_in;  /* float2 [max_len + 2] */
     void *d_out; /* float2 [max_len + 2] */
@@ -89,6 +90,7 @@ static void fir_core_free(struct fir_core *f) {
         cudaStreamDestroy(f->stream);
     }
     cudaFree(f->d_taps);
+    free(f->h_taps);
     cudaFree(f->d_hist[0]);
     cudaFree(f->d_hist[1]);
     cudaFree(f->d_in);
@@ -113,6 +115,7 @@ static int fir_core_init(struct fir_core *f, uint8_t decimation, const float *ta
         f->hist_len = 2;
     }
     int code = sdrm_upload_taps_dup(taps, taps_len, &f->d_taps);
+    f->h_taps = sdrm_host_taps_dup(taps, taps_len);
     const size_t cap = sdrm_round_up(max_len, 2) + 2;
     for (int i = 0; i < 2 && code == 0; i++) {
         code = sdrm_dev_zalloc(&f->d_hist[i], (size_t) f->hist_len * 8);
@@ -160,6 +163,7 @@ static void fir_core_process(struct fir_core *f, const void *input, size_t input
     a.hist = f->d_hist[f->cur];
     a.hist_len = f->hist_len;
     a.taps_dup = f->d_taps;
+    a.h_taps_dup = f->h_taps;
     a.n_taps = f->n_taps;
     a.decimation = dec;
     a.phase = f->phase;

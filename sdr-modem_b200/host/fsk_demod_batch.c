@@ -41,6 +41,8 @@ struct sdrm_fsk_demod_batch_t {
 
     /* lpf1 + quad */
     void *d_taps1;
+    float *h_taps1; /* host copies of the (h, h) pairs */
+    float *h_taps2;
     int t1;
     int hist1_len;
     void *d_hist1[2];
@@ -153,6 +155,7 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
     if (code != 0) goto fail;
     b->t1 = (int) taps_len;
     code = sdrm_upload_taps_dup(taps, taps_len, &b->d_taps1);
+    b->h_taps1 = sdrm_host_taps_dup(taps, taps_len);
     free(taps);
     taps = NULL;
     if (code != 0) goto fail;
@@ -171,6 +174,7 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
     if (code != 0) goto fail;
     b->t2 = (int) taps_len;
     code = sdrm_upload_taps_dup(taps, taps_len, &b->d_taps2);
+    b->h_taps2 = sdrm_host_taps_dup(taps, taps_len);
     free(taps);
     taps = NULL;
     if (code != 0) goto fail;
@@ -321,6 +325,7 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     f1.hist = b->d_hist1[b->hist1_cur];
     f1.hist_len = b->hist1_len;
     f1.taps_dup = b->d_taps1;
+    f1.h_taps_dup = b->h_taps1;
     f1.n_taps = b->t1;
     f1.decimation = 1;
     f1.phase = 0;
@@ -360,6 +365,7 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     f2.hist = b->d_hist2[b->hist2_cur];
     f2.hist_len = b->hist2_len;
     f2.taps_dup = b->d_taps2;
+    f2.h_taps_dup = b->h_taps2;
     f2.n_taps = b->t2;
     f2.decimation = dec;
     f2.phase = b->phase2;
@@ -686,6 +692,8 @@ void sdrm_fsk_demod_batch_destroy(sdrm_fsk_demod_batch *b) {
     cudaSetDevice(b->device);
     cudaDeviceSynchronize();
     cudaFree(b->d_taps1);
+    free(b->h_taps1);
+    free(b->h_taps2);
     cudaFree(b->d_taps2);
     cudaFree(b->d_atan);
     cudaFree(b->d_mmse);

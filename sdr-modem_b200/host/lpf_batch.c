@@ -22,6 +22,7 @@ struct sdrm_lpf_batch_t {
     int phase;
     int cur;
     void *d_taps;
+    float *h_taps; /* host copy of the (h, h) pairs */
     void *d_hist[2];
     size_t stride;      /* float2 per row of the internal buffers */
     void *d_pair_in;    /* real streams: interleaved input */
@@ -65,6 +66,7 @@ int sdrm_lpf_batch_create(uint32_t n_channels, uint8_t decimation, uint64_t samp
     }
     b->stride = sdrm_round_up((size_t) max_input_buffer_length, 2) + 2;
     if (code == 0) code = sdrm_upload_taps_dup(taps, taps_len, &b->d_taps);
+    if (code == 0) b->h_taps = sdrm_host_taps_dup(taps, taps_len);
     free(taps);
     for (int i = 0; i < 2 && code == 0; i++) {
         code = sdrm_dev_zalloc(&b->d_hist[i], (size_t) b->rows * b->hist_len * 8);
@@ -128,6 +130,7 @@ int sdrm_lpf_batch_process_device(sdrm_lpf_batch *b, const void *d_input, size_t
     a.hist = b->d_hist[b->cur];
     a.hist_len = b->hist_len;
     a.taps_dup = b->d_taps;
+    a.h_taps_dup = b->h_taps;
     a.n_taps = b->n_taps;
     a.decimation = dec;
     a.phase = b->phase;
@@ -211,6 +214,7 @@ void sdrm_lpf_batch_destroy(sdrm_lpf_batch *b) {
         cudaStreamDestroy(b->stream);
     }
     cudaFree(b->d_taps);
+    free(b->h_taps);
     cudaFree(b->d_hist[0]);
     cudaFree(b->d_hist[1]);
     cudaFree(b->d_pair_in);

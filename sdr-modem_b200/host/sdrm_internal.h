@@ -56,6 +56,8 @@ int sdrm_convolve_full(const float *x, size_t x_len, const float *y, size_t y_le
 
 /* Uploads taps reversed and duplicated into float2 (h, h), padded with zeros to an even count + 2. */
 int sdrm_upload_taps_dup(const float *taps, size_t len, void **d_taps);
+/* The same (h, h) pairs, len float2, in host memory (malloc): short filters pass them to the kernel as parameters. */
+float *sdrm_host_taps_dup(const float *taps, size_t len);
 
 /* Markstein corrections needed so that the tail's division by `length` is an IEEE division (exhaustive check, ~20 ms). */
 int sdrm_division_steps(int length);

@@ -145,6 +145,19 @@ int sdrm_upload_taps_dup(const float *taps, size_t len, void **d_taps) {
     return code;
 }
 
+float *sdrm_host_taps_dup(const float *taps, size_t len) {
+    float *dup = malloc((len == 0 ? 1 : len) * 2 * sizeof(float));
+    if (dup == NULL) {
+        return NULL;
+    }
+    for (size_t j = 0; j < len; j++) {
+        const float h = taps[len - 1 - j]; /* reversed, as fir_filter.c:27 */
+        dup[2 * j] = h;
+        dup[2 * j + 1] = h;
+    }
+    return dup;
+}
+
 /*
  * How many Markstein corrections the tail kernel's division by `length` needs to round like an IEEE division:
  * q0 = RN(a * rcp), e = fma(-q, L, a), q' = fma(e, rcp, q). Inside the exponent range the kernel accepts nothing
