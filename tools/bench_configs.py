@@ -4,6 +4,7 @@
   python tools/bench_configs.py --config c4 [--channels 1024]   gfsk_mod batch, 2048-byte packets, sps 2 (configs[3])
   python tools/bench_configs.py --config c1                      one channel on one host core, reference CPU chain (configs[0])
   python tools/bench_configs.py --config c3alt                   configs[2] recomposed as doppler -> decimating lpf -> fsk_demod
+  python tools/bench_configs.py --config perf                    the reference's perf_fsk_modem shape (48 ksps, 4800 baud) as a batch
   python tools/bench_configs.py --config c3 [--channels 4096]   doppler + GMSK 2400 baud from 2.4 Msps, decim 100 (configs[2])
 
 Each prints one JSON line with the device-resident throughput, the roofline that bounds the stage, and the reference's
@@ -160,6 +161,57 @@ def bench_c3(args):
         "cpu_baseline": cpu, "error_flags": demod.error_flags()}))
 
 
+def bench_perf_shape(args):
+    """The reference's own perf_fsk_modem demodulator shape (test/perf_fsk_modem.c:72: 48 ksps, 4800 baud, decimation 2: T1 = 157,
+    T2 = 57, 5 samples per symbol after decimation) as a batch of 1024 channels: the filters are light here and the serial tail
+    (dc blocker + clock recovery) is what bounds the step."""
+    import torch
+    import sdrm
+    from oracle import ref
+    import workloads
+    n_ch, chunk = args.channels or 1024, 131072
+    shape = workloads.DemodShape("perf_fsk_modem 4800@48k/chunk131072", 48000, 4800, 5000, 2, 2000, True, chunk)
+    flops, t1, t2 = workloads.demod_flops_per_sample(shape)
+    iq = workloads.gfsk_channels(n_ch, 2 * chunk, shape, seed=1000, device="cuda")
+    bufs = [iq[:, :chunk].contiguous(), iq[:, chunk:].contiguous()]
+    demod = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=int(chunk / 10 * 1.2) + 64)
+    fir, tail = torch.cuda.ExternalStream(demod.stream), torch.cuda.ExternalStream(demod.tail_stream)
+
+    def step(k):
+        demod.process_device(bufs[k % 2].data_ptr(), chunk, chunk)
+        demod.release()
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(fir)
+    for k in range(args.steps):
+        step(k)
+    end.record(tail)
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / args.steps
+    value = n_ch * chunk / (ms * 1e-3) / 1e6
+    demod.set_profiling(True)
+    step(0)
+    stage = demod.stage_times()
+    cpu = None
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        x = workloads.gfsk_channels(cores, 2 * chunk, shape, seed=1000, device="cpu").numpy()
+        sec, _ = ref.bench_fsk_demod(*shape.create_args, chunk, x, cores, passes=4)
+        cpu = {"value": cores * 2 * chunk * 4 / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+               "sample": "%d channels x %d samples x 4 passes, one thread per channel" % (cores, 2 * chunk)}
+    print(json.dumps({
+        "metric": "demodulated Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d channels x %s, dc on (the reference's perf_fsk_modem shape); T1 = %d, T2 = %d"
+                               % (n_ch, shape.name, t1, t2), "mode": "exact", "flop_per_sample": flops},
+        "roofline": {"bound": "serial tail (dependent-issue latency), not a throughput roofline",
+                     "stage_ms": {"lpf1_quad": stage[0], "lpf2": stage[1], "dc_clock_tail": stage[2]}},
+        "cpu_baseline": cpu, "error_flags": demod.error_flags()}))
+
+
 def bench_c1(args):
     """BASELINE configs[0]: ONE channel on ONE host core through the reference's own CPU chain (oracle/_ref), 10 s of signal in
     4096-sample calls; plus the reference's published perf shape (test/perf_fsk_modem.c: 48 kHz, 4800 baud, input (uint8) i)."""
@@ -245,7 +297,7 @@ def bench_c3alt(args):
 
 def main():
     p = argparse.ArgumentParser()
-    p.add_argument("--config", required=True, choices=["c1", "c3", "c3alt", "c4"])
+    p.add_argument("--config", required=True, choices=["c1", "c3", "c3alt", "c4", "perf"])
     p.add_argument("--channels", type=int, default=None)
     p.add_argument("--steps", type=int, default=None)
     p.add_argument("--warmup", type=int, default=3)
@@ -261,6 +313,9 @@ def main():
         args.channels = args.channels or 1024
         args.steps = args.steps or 10
         bench_c3alt(args)
+    elif args.config == "perf":
+        args.steps = args.steps or 20
+        bench_perf_shape(args)
     else:
         args.channels = args.channels or 4096
         args.steps = args.steps or 3
