@@ -481,6 +481,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
     float last_sample = st.last_sample;
     bool overflow = false;
 
+    const uint32_t taps_base = smem_u32(s.taps);
     __syncthreads();
     for (int t = 0; t < n_steps; t++) {
         if (warp < PROD) {
@@ -519,9 +520,15 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                     overflow = true;
                     break;
                 }
-                const int imu = __float2int_rn(__fmul_rn(mu, 128.0f));
-                const float4 t_lo = *reinterpret_cast<const float4 *>(s.taps + imu * 8);
-                const float4 t_hi = *reinterpret_cast<const float4 *>(s.taps + imu * 8 + 4);
+                // imu = (int) rint(mu * 128) (mmse_fir_interpolator.c:189), mu in [0, 1): mu * 128 is exact, and adding 1.5 * 2^23
+                // rounds it to an integer (to nearest even, like rint) in the low mantissa bits: one FFMA on the loop's critical
+                // path instead of a multiply and a conversion. A NaN mu gives row 0, as the conversion does.
+                const int imu = __float_as_int(__fmaf_rn(mu, 128.0f, 12582912.0f)) & 0xff;
+                // the tap row through an explicit shared-memory address: with a generic pointer the compiler rebuilds the
+                // shared window base (S2UR + ULEA, ~20 cycles on the critical path) in every iteration
+                float4 t_lo, t_hi;
+                asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t_lo.x), "=f"(t_lo.y), "=f"(t_lo.z), "=f"(t_lo.w) : "r"(taps_base + imu * 32));
+                asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(t_hi.x), "=f"(t_hi.y), "=f"(t_hi.z), "=f"(t_hi.w) : "r"(taps_base + imu * 32));
                 const float tp[8] = {t_lo.x, t_lo.y, t_lo.z, t_lo.w, t_hi.x, t_hi.y, t_hi.z, t_hi.w};
                 // 11 samples from ii - 3 on; the mirror rows make the window contiguous
                 const float *win = ring_lane + ((ii - 3 - history) & ring_mask) * 32;
