@@ -123,7 +123,7 @@ __device__ __forceinline__ void fir_d1_body(float2 (&acc)[kR], float4 (&w)[6], c
 #pragma unroll
     for (int u = 0; u < 12; u++) {
         if (!GUARD || j + u < n_taps) {
-            float2 h = TP ? p.taps_c[ju + u] : hs[j + u];
+            float2 h = TP ? p.taps_c[(FAST ? ju : j) + u] : hs[j + u];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
                 const int e = (u + r) % 12;
@@ -166,14 +166,14 @@ __device__ __forceinline__ void fir_d2_body(float2 (&acc)[kR], float4 (&w)[11], 
 #pragma unroll
     for (int q = 0; q < 11; q++) {
         if (!GUARD || j + 2 * q < n_taps) {
-            float2 h = TP ? p.taps_c[ju + 2 * q] : hs[j + 2 * q];
+            float2 h = TP ? p.taps_c[(FAST ? ju : j) + 2 * q] : hs[j + 2 * q];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
                 acc[r] = mac2<FAST>(acc[r], lo(w[(q + r) % 11]), h, one, negzero);
             }
         }
         if (!GUARD || j + 2 * q + 1 < n_taps) {
-            float2 h = TP ? p.taps_c[ju + 2 * q + 1] : hs[j + 2 * q + 1];
+            float2 h = TP ? p.taps_c[(FAST ? ju : j) + 2 * q + 1] : hs[j + 2 * q + 1];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
                 acc[r] = mac2<FAST>(acc[r], hi(w[(q + r) % 11]), h, one, negzero);
@@ -598,10 +598,12 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
     if ((((uintptr_t) a->in | (uintptr_t) a->hist | (uintptr_t) a->taps_dup) & 15) != 0 || (a->in_stride & 1)) {
         return -22;  // TMA bulk copies need 16-byte aligned rows
     }
-    // short filters in FMA mode: the taps travel in the kernel parameters (see FirParams::taps_c). Not in exact mode: its FFMA2 pair
-    // already takes -0 and 1 from uniform registers, an instruction has one uniform operand, and with h in that place K1 is 2 % slower
-    // (7.65 against 7.49 ms); FMA mode goes from 4.78 to 3.97 ms (71 -> 86 % of the FMA peak).
-    const bool taps_in_params = a->fast && a->h_taps_dup != nullptr && n_blocks == 1;
+    // Short filters carry their taps in the kernel parameters (see FirParams::taps_c). FMA mode indexes them with a counter of its
+    // own, which the compiler keeps in a uniform register: uniform loads, h as the FFMA2's uniform operand, K1 4.78 -> 3.97 ms. Exact
+    // mode indexes them with the sample counter and gets a register-indexed constant load into ordinary registers: its FFMA2 pair
+    // already takes -0 and 1 from uniform registers and an instruction has one uniform operand (h there: 7.65 ms), but the constant
+    // load still saves the shared-memory load per tap and warp: K1 7.50 -> 7.45 ms, lpf2 0.966 -> 0.947 ms.
+    const bool taps_in_params = a->h_taps_dup != nullptr && n_blocks == 1;
     if (taps_in_params) {
         memcpy(p.taps_c, a->h_taps_dup, (size_t) a->n_taps * sizeof(float2));
         for (int j = a->n_taps; j < kTapBlock; j++) {
