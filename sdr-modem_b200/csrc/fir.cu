@@ -26,10 +26,19 @@
 
 namespace {
 
+#ifndef FIR_R
+#define FIR_R 10
+#define FIR_TAPBLOCK 528
+#define FIR_CTAS1 3
+#define FIR_CTAS2 2
+#endif
 constexpr int kThreads = 256;
-constexpr int kR = 10;                    // outputs per thread
+constexpr int kR = FIR_R;                 // outputs per thread (even)
 constexpr int kTile = kThreads * kR;      // outputs per CTA
-constexpr int kTapBlock = 528;            // multiple of 12 (D=1 window period) and 22 (D=2 window period)
+constexpr int kW1 = kR + 2;               // D=1: samples in the register window = taps per window period
+constexpr int kW2 = kR + 1;               // D=2: sample pairs in the register window; 2 * kW2 taps per window period
+constexpr int kTapBlock = FIR_TAPBLOCK;   // multiple of kW1 and 2 * kW2 (528 = 44 * 12 = 24 * 22 for 10 outputs per thread)
+static_assert(kTapBlock % kW1 == 0 && kTapBlock % (2 * kW2) == 0 && kR % 2 == 0, "tap block must hold whole window periods");
 constexpr int kSlack = 32;                // float2 of read-ahead slack after each staged sample window
 
 struct FirParams {
@@ -118,21 +127,21 @@ __device__ __forceinline__ float2 hi(const float4 &v) { return make_float2(v.z, 
 
 // ---- decimation 1: acc[r] += s[j + r] * h[j]; register window of 12 samples, period 12 taps -------------------
 template <bool FAST, bool ALIGNED, bool GUARD, bool TP>
-__device__ __forceinline__ void fir_d1_body(float2 (&acc)[kR], float4 (&w)[6], const float2 *s, const float2 *hs, const FirParams &p,
+__device__ __forceinline__ void fir_d1_body(float2 (&acc)[kR], float4 (&w)[kW1 / 2], const float2 *s, const float2 *hs, const FirParams &p,
                                             int j, int ju, int n_taps, float2 one, float2 negzero) {
 #pragma unroll
-    for (int u = 0; u < 12; u++) {
+    for (int u = 0; u < kW1; u++) {
         if (!GUARD || j + u < n_taps) {
             float2 h = TP ? p.taps_c[(FAST ? ju : j) + u] : hs[j + u];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
-                const int e = (u + r) % 12;
+                const int e = (u + r) % kW1;
                 float2 x = (e & 1) ? hi(w[e >> 1]) : lo(w[e >> 1]);
                 acc[r] = mac2<FAST>(acc[r], x, h, one, negzero);
             }
             if (u & 1) {
-                // samples j+u-1 and j+u are no longer needed: refill their slots with j+u+11, j+u+12
-                w[(u - 1) >> 1] = ld_pair<ALIGNED>(s + j + u + 11);
+                // samples j+u-1 and j+u are no longer needed: refill their slots with the pair one window further on
+                w[(u - 1) >> 1] = ld_pair<ALIGNED>(s + j + u + kW1 - 1);
             }
         }
     }
@@ -141,9 +150,9 @@ __device__ __forceinline__ void fir_d1_body(float2 (&acc)[kR], float4 (&w)[6], c
 template <bool FAST, bool ALIGNED, bool TP>
 __device__ __forceinline__ void fir_d1_block(float2 (&acc)[kR], const float2 *s, const float2 *hs, const FirParams &p, int n_taps,
                                              float2 one, float2 negzero) {
-    float4 w[6];
+    float4 w[kW1 / 2];
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < kW1 / 2; k++) {
         w[k] = ld_pair<ALIGNED>(s + 2 * k);
     }
     int j = 0;
@@ -151,7 +160,7 @@ __device__ __forceinline__ void fir_d1_block(float2 (&acc)[kR], const float2 *s,
     // so that it can live in a uniform register and the taps be loaded into uniform registers
     int ju;
     asm volatile("mov.u32 %0, 0;" : "=r"(ju));
-    for (; j + 12 <= n_taps; j += 12, ju += 12) {
+    for (; j + kW1 <= n_taps; j += kW1, ju += kW1) {
         fir_d1_body<FAST, ALIGNED, false, TP>(acc, w, s, hs, p, j, ju, n_taps, one, negzero);
     }
     if (j < n_taps) {
@@ -161,26 +170,26 @@ __device__ __forceinline__ void fir_d1_block(float2 (&acc)[kR], const float2 *s,
 
 // ---- decimation 2: acc[r] += s[j + 2r] * h[j]; even/odd windows of 11 samples each, period 22 taps ------------
 template <bool FAST, bool ALIGNED, bool GUARD, bool TP>
-__device__ __forceinline__ void fir_d2_body(float2 (&acc)[kR], float4 (&w)[11], const float2 *s, const float2 *hs, const FirParams &p,
+__device__ __forceinline__ void fir_d2_body(float2 (&acc)[kR], float4 (&w)[kW2], const float2 *s, const float2 *hs, const FirParams &p,
                                             int j, int ju, int n_taps, float2 one, float2 negzero) {
 #pragma unroll
-    for (int q = 0; q < 11; q++) {
+    for (int q = 0; q < kW2; q++) {
         if (!GUARD || j + 2 * q < n_taps) {
             float2 h = TP ? p.taps_c[(FAST ? ju : j) + 2 * q] : hs[j + 2 * q];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
-                acc[r] = mac2<FAST>(acc[r], lo(w[(q + r) % 11]), h, one, negzero);
+                acc[r] = mac2<FAST>(acc[r], lo(w[(q + r) % kW2]), h, one, negzero);
             }
         }
         if (!GUARD || j + 2 * q + 1 < n_taps) {
             float2 h = TP ? p.taps_c[(FAST ? ju : j) + 2 * q + 1] : hs[j + 2 * q + 1];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
-                acc[r] = mac2<FAST>(acc[r], hi(w[(q + r) % 11]), h, one, negzero);
+                acc[r] = mac2<FAST>(acc[r], hi(w[(q + r) % kW2]), h, one, negzero);
             }
         }
         if (!GUARD || j + 2 * q + 2 < n_taps) {
-            w[q] = ld_pair<ALIGNED>(s + j + 2 * q + 22);
+            w[q] = ld_pair<ALIGNED>(s + j + 2 * q + 2 * kW2);
         }
     }
 }
@@ -188,15 +197,15 @@ __device__ __forceinline__ void fir_d2_body(float2 (&acc)[kR], float4 (&w)[11], 
 template <bool FAST, bool ALIGNED, bool TP>
 __device__ __forceinline__ void fir_d2_block(float2 (&acc)[kR], const float2 *s, const float2 *hs, const FirParams &p, int n_taps,
                                              float2 one, float2 negzero) {
-    float4 w[11];
+    float4 w[kW2];
 #pragma unroll
-    for (int k = 0; k < 11; k++) {
+    for (int k = 0; k < kW2; k++) {
         w[k] = ld_pair<ALIGNED>(s + 2 * k);
     }
     int j = 0;
     int ju;
     asm volatile("mov.u32 %0, 0;" : "=r"(ju));
-    for (; j + 22 <= n_taps; j += 22, ju += 22) {
+    for (; j + 2 * kW2 <= n_taps; j += 2 * kW2, ju += 2 * kW2) {
         fir_d2_body<FAST, ALIGNED, false, TP>(acc, w, s, hs, p, j, ju, n_taps, one, negzero);
     }
     if (j < n_taps) {
@@ -246,7 +255,7 @@ __device__ void stage_load(const FirParams &p, int row, long long start, int cou
 }
 
 template <int D, bool FAST, bool ALIGNED, bool TP>
-__global__ void __launch_bounds__(kThreads, D == 1 ? 3 : 2) fir_tile_kernel(const FirParams p) {
+__global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_tile_kernel(const FirParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[2];
     __shared__ float2 last_out[kThreads];
