@@ -518,17 +518,14 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
             const int done_blocks = t - PROD + 1;
             const int avail = history + (done_blocks <= 0 ? 0 : min(a.n_rows, done_blocks * kBlockRows));
             // The body is branch-free: the reference's three data-dependent paths (leading zero taps, NaN output, loop
-            // update) are computed side by side and selected, and so is the loop itself: the warp makes as many trips as its
-            // busiest lane needs (3 or 4 per step at 10 samples per symbol), lanes that have nothing left in this step run
-            // along with their stores and state updates switched off. Control flow is then uniform — no divergence
-            // bookkeeping around a trip whose dependent chain is all the warp has to do.
-            for (;;) {
-                bool go = run_clock && ii >= 0 && ii + 7 < avail && oo < a.max_out;
-                if (go && avail + kBlockRows - (ii - 3) > a.ring_slots) {  // the lane fell behind its ring (pathological input)
+            // update) are computed side by side and selected, so that lanes in different situations stay converged and the
+            // iteration is one dependent chain of ~40 operations instead of a sequence of divergent regions.
+            // (A variant in which every lane makes the warp's trips with its stores and updates switched off was measured:
+            // idle lanes must then be kept away from ring rows that are still being written, and the extra select on the
+            // window address costs more than the uniform control flow saves.)
+            while (run_clock && ii >= 0 && ii + 7 < avail && oo < a.max_out) {
+                if (avail + kBlockRows - (ii - 3) > a.ring_slots) {  // the lane fell behind its ring (pathological input)
                     overflow = true;
-                    go = false;
-                }
-                if (!__any_sync(0xffffffffu, go)) {
                     break;
                 }
                 // imu = (int) rint(mu * 128) (mmse_fir_interpolator.c:189), mu in [0, 1): mu * 128 is exact, and adding 1.5 * 2^23
@@ -541,8 +538,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                 asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t_lo.x), "=f"(t_lo.y), "=f"(t_lo.z), "=f"(t_lo.w) : "r"(taps_base + imu * 32));
                 asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(t_hi.x), "=f"(t_hi.y), "=f"(t_hi.z), "=f"(t_hi.w) : "r"(taps_base + imu * 32));
                 const float tp[8] = {t_lo.x, t_lo.y, t_lo.z, t_lo.w, t_hi.x, t_hi.y, t_hi.z, t_hi.w};
-                // 11 samples from ii - 3 on; the mirror rows make the window contiguous (an idle lane reads whatever its
-                // stale index points at inside the ring)
+                // 11 samples from ii - 3 on; the mirror rows make the window contiguous
                 const float *win = ring_lane + ((ii - 3 - history) & ring_mask) * 32;
                 float v[11];
 #pragma unroll
@@ -563,27 +559,24 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                 }
                 const bool nan = isnan(acc);  // clock_recovery_mm.c:107-113: output 0, skip the loop update
                 const float out = nan ? 0.0f : acc;
-                if (go) {
-                    if (soft != nullptr) soft[oo] = out;
-                    if (hard != nullptr) {
-                        // fsk_demod.c:106, volk_32f_s32f_convert_8i: saturate(rint(x * 127)). The clamped value plus 1.5 * 2^23
-                        // carries rint(x) in two's complement in its low mantissa bits (out is never NaN here).
-                        const float scaled = fminf(fmaxf(__fmul_rn(out, 127.0f), -128.0f), 127.0f);
-                        hard[oo] = (int8_t) (__float_as_int(__fadd_rn(scaled, 12582912.0f)) & 0xff);
-                    }
+                if (soft != nullptr) soft[oo] = out;
+                if (hard != nullptr) {
+                    // fsk_demod.c:106, volk_32f_s32f_convert_8i: saturate(rint(x * 127)). The clamped value plus 1.5 * 2^23
+                    // carries rint(x) in two's complement in its low mantissa bits (out is never NaN here).
+                    const float scaled = fminf(fmaxf(__fmul_rn(out, 127.0f), -128.0f), 127.0f);
+                    hard[oo] = (int8_t) (__float_as_int(__fadd_rn(scaled, 12582912.0f)) & 0xff);
                 }
                 const float mm_val = __fsub_rn(__fmul_rn(slice_pm1(last_sample), out), __fmul_rn(slice_pm1(out), last_sample));
                 float omega_next = __fadd_rn(omega, __fmul_rn(a.gain_omega, mm_val));
                 omega_next = __fadd_rn(a.omega_mid, branchless_clip(__fsub_rn(omega_next, a.omega_mid), a.omega_lim));
                 const float mu_next = __fadd_rn(__fadd_rn(mu, omega_next), __fmul_rn(a.gain_mu, mm_val));
                 const float whole = floorf(nan ? omega : mu_next);
-                const bool update = go && !nan;
-                previous = go ? ii : previous;
-                ii += go ? (int) whole : 0;
-                last_sample = update ? out : last_sample;
-                mu = update ? __fsub_rn(mu_next, whole) : mu;
-                omega = update ? omega_next : omega;
-                oo += go ? 1 : 0;
+                previous = ii;
+                ii += (int) whole;
+                last_sample = nan ? last_sample : out;
+                mu = nan ? mu : __fsub_rn(mu_next, whole);
+                omega = nan ? omega : omega_next;
+                oo++;
             }
         }
         __syncthreads();
