@@ -7,12 +7,17 @@
 
 One step = one call of the demod chain (lpf1 -> quadrature demod -> lpf2 -> dc blocker -> clock recovery -> int8)
 over `chunk` new samples of every channel. `value` counts input complex samples per second with the inputs resident
-in HBM; `e2e` is the same through the host-buffer C-ABI call (pinned host input, H2D and D2H inside the timed region).
-Channels are sharded across ranks (weak scaling: `--channels` per GPU), there is no collective on the data path.
-Prints ONE JSON line on rank 0.
+in HBM and the int8 results copied back to pinned host memory inside the timed loop; `e2e` is the same through the
+host-buffer C-ABI call (pinned host input, H2D and D2H inside the timed region), beside a plain-copy probe of what the
+host gives that many GPUs at once. Channels are sharded across ranks (weak scaling: `--channels` per GPU), there is no
+collective on the data path. Prints ONE JSON line on rank 0.
+
+The line also carries, outside every timed region (rank 0): the FMA arithmetic mode with its measured parity counts against
+the strict reference build (`roofline.fma_*`), the reference's CPU chain on the host cores (`cpu_baseline`, strict and
+tuned builds), and the other BASELINE.json configs (`configs`: modulator, Doppler + 2.4 Msps chain, one CPU channel, and on 8
+GPUs the 32768-channel job), each with its own roofline fraction and CPU baseline.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -25,6 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "sdr-modem_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 METRIC = "demodulated Msamples/s"
 UNIT = "Msamples/s"
@@ -42,8 +48,11 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-fma-line", action="store_true", help="skip the extra measurement in the FMA arithmetic mode")
-    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--no-parity", action="store_true", help="skip the fast-mode parity counts (CPU reference runs)")
+    p.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (C1, C3 subset, C4, C5)")
+    p.add_argument("--cpu-seconds", type=float, default=10.0)
     p.add_argument("--debug-no-tail", action="store_true", help="measurement aid: skip the serial tail (invalid result)")
+    p.add_argument("--full-line", default=None, help="also write the JSON line to this file")
     return p.parse_args()
 
 
@@ -119,33 +128,58 @@ def measured_peaks():
 
 def k1_traffic(samples_per_launch):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, scaled to this launch."""
-    path = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        t = json.load(f)
-    per_sample = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["samples_per_launch"]
-    return per_sample * samples_per_launch
+    for name in ("r2_k1_traffic.json", "r1_k1_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as f:
+                t = json.load(f)
+            per_sample = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["samples_per_launch"]
+            return per_sample * samples_per_launch
+    return None
 
 
-def cpu_reference_run(shape, seconds, n_threads=None):
-    """The reference's own CPU chain (oracle/_ref, strict build) driven like dsp_worker: one pthread per channel."""
-    import torch
+def c2_shape(chunk):
+    import workloads
+    return workloads.DemodShape("gmsk9600@192k/chunk%d" % chunk, 192000, 9600, 5000, 2, 2000, True, chunk)
+
+
+def c2_config(args, shape, mode):
+    """The `config` of the line: identical in the b200 arm and the reference arm (the reference arm times a bounded sample of
+    this workload and says so in cpu_baseline.sample)."""
+    import workloads
+    flops, t1, t2 = workloads.demod_flops_per_sample(shape)
+    return {"workload": "%d channels/GPU x %s, GMSK BT 0.5, Eb/N0 12 dB, dev 5 kHz, decim 2, dc on (BASELINE configs[1])"
+                        % (args.channels, shape.name),
+            "channels_per_gpu": args.channels, "chunk": args.chunk, "mode": mode,
+            "parallelism": "channels sharded, no collective",
+            "l2": "inputs larger than L2 (2 x %.2f GiB rotating)" % (args.channels * args.chunk * 8 / 2 ** 30),
+            "flop_per_sample": flops, "t1": t1, "t2": t2,
+            "generator": "workloads.gfsk_channels: torch RNG payload, Gaussian pulse by conv1d, per-channel carrier/timing offset, "
+                         "AWGN (same statistics as SURVEY 8d's xorshift + oracle gfsk_mod recipe, not its bytes; both arms and the "
+                         "parity checks read the same samples)"}
+
+
+def cpu_reference_run(shape, seconds, n_threads=None, build=False):
+    """The reference's own CPU chain (oracle/_ref) driven like dsp_worker: one pthread per channel. build: False = strict
+    (the parity-defining build), "tuned" = -O3 + lane-partial dot products (SIMD VOLK stand-in, baseline only)."""
     from oracle import ref
     import workloads
-    if not ref.available():
+    if not ref.available(build):
         return None
     cores = n_threads or os.cpu_count() or 1
     n = shape.chunk * 2
     iq = workloads.gfsk_channels(cores, n, shape, seed=1000, device="cpu").numpy()
     # calibrate with one pass, then size the timed run
-    sec, _ = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=1)
+    sec, _ = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=1, fma=build)
     passes = max(1, int(seconds / max(sec, 1e-3)))
-    sec, symbols = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=passes)
+    sec, symbols = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=passes, fma=build)
     samples = cores * n * passes
+    flavour = ("oracle/_ref tuned build v%d (-O3 -march=x86-64-v%d -ffp-contract=fast, lane-partial SIMD dot products: stand-in for "
+               "SIMD VOLK, not bit-identical)" % (ref.tuned_level(), ref.tuned_level())) if build == "tuned" else \
+        "oracle/_ref strict build (-O2 -ffp-contract=off, VOLK generic shim)"
     return {"value": samples / sec / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": "%d channels x %d samples x %d passes, chunk %d, %.1f s, oracle/_ref strict build (-O2 -ffp-contract=off, VOLK generic shim)"
-                      % (cores, n, passes, shape.chunk, sec),
+            "sample": "%d channels (one per thread) x %d samples x %d passes, chunk %d, %.1f s, %s; compared per sample, so the "
+                      "channel count of the sample does not enter the ratio" % (cores, n, passes, shape.chunk, sec, flavour),
             "seconds": sec, "symbols": int(symbols)}
 
 
@@ -162,15 +196,20 @@ def claim_stdout():
         os.dup2(2, 1)
 
 
-def emit_line(line):
+def emit_line(line, also=None):
     data = (json.dumps(line) + "\n").encode()
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+    if also:
+        with open(also, "wb") as f:
+            f.write(data)
 
 
 def run_reference_arm(args, shape):
     """bench.py --impl reference: the reference's own CPU chain (oracle/_ref, built from the reference sources in place) on all
-    host cores, same metric and workload shape; a step is a bounded sample (a few passes of 16 x 2 chunks), so that
-    K steps + W warm-ups end within a few minutes."""
+    host cores, same metric and `config` as the b200 arm; a step is a bounded sample of that workload (one channel per core,
+    2 chunks, a few passes), so that K steps + W warm-ups end within a few minutes. Both CPU builds are timed, the strict one
+    (what the reference's tests pin, VOLK_GENERIC=1) and the tuned one (stand-in for SIMD VOLK); `value` is the FASTER of
+    the two, so that the driver's ratio is against the best CPU figure available here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -182,34 +221,196 @@ def run_reference_arm(args, shape):
     cores = os.cpu_count() or 1
     n = shape.chunk * 2
     iq = workloads.gfsk_channels(cores, n, shape, seed=1000, device="cpu").numpy()
-    sec, _ = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=1)
-    target = max(0.2, args.cpu_seconds / max(1, args.steps))
-    passes = max(1, int(round(target / max(sec, 1e-3))))
-    for _ in range(args.warmup):
-        ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=1)
-    total_sec, total_samples = 0.0, 0
-    for _ in range(args.steps):
-        sec, _ = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=passes)
-        total_sec += sec
-        total_samples += cores * n * passes
-    value = total_samples / total_sec / 1e6
-    sample = ("%d channels x %d samples x %d passes per step, chunk %d, oracle/_ref strict build (-O2 -ffp-contract=off, VOLK "
-              "generic shim), one thread per channel" % (cores, n, passes, shape.chunk))
+    builds = [False] + (["tuned"] if ref.available("tuned") and ref.tuned_level() else [])
+    results = {}
+    for build in builds:
+        sec, _ = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=1, fma=build)
+        target = max(0.2, args.cpu_seconds / len(builds) / max(1, args.steps))
+        passes = max(1, int(round(target / max(sec, 1e-3))))
+        for _ in range(args.warmup):
+            ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=1, fma=build)
+        total_sec, total_samples = 0.0, 0
+        for _ in range(args.steps):
+            sec, _ = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, cores, passes=passes, fma=build)
+            total_sec += sec
+            total_samples += cores * n * passes
+        results["tuned" if build else "strict"] = (total_samples / total_sec / 1e6, total_sec, passes)
+    best = max(results, key=lambda k: results[k][0])
+    value, total_sec, passes = results[best]
+    sample = ("%d channels (one per thread) x %d samples x %d passes per step, chunk %d; value = the faster of the CPU builds "
+              "(%s); strict = oracle/_ref -O2 -ffp-contract=off VOLK generic shim (parity-defining), tuned = -O3 "
+              "x86-64-v%d lane-partial SIMD dot products (SIMD VOLK stand-in); per-sample rate, the sample's channel count does "
+              "not enter" % (cores, n, passes, shape.chunk, best, ref.tuned_level()))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_sec / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d channels x %s, GMSK BT 0.5, Eb/N0 12 dB, dev 5 kHz, decim 2, dc on (BASELINE configs[1], "
-                                   "bounded sample)" % (cores, shape.name), "channels": cores, "chunk": shape.chunk},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "config": c2_config(args, shape, args.mode),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                             "build": best, "strict_value": results["strict"][0],
+                             "tuned_value": results["tuned"][0] if "tuned" in results else None},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    emit_line(line)
+    emit_line(line, args.full_line)
+
+
+def fast_mode_parity(sdrm, shape, bufs, n_channels, cap, device):
+    """Counts of the north-star epsilon rule for the FMA mode against the STRICT reference build (checker only, outside every
+    timed region): the first n_channels channels of the resident bench input (2 calls of `chunk` samples = 1.37 s of signal per
+    channel at the defaults) and the four golden files of the reference's test_fsk_demod.c."""
+    import torch
+    from oracle import parity, ref
+    if not ref.available():
+        return None
+    chunk = shape.chunk
+    sub = [b[:n_channels].contiguous() for b in bufs]
+    iq = torch.cat(sub, dim=1).cpu().numpy()
+    batch = sdrm.FskDemodBatch(n_channels, *shape.create_args, chunk, max_symbols_per_call=cap, fast=True, soft=True, device=device)
+    got_hard = [[] for _ in range(n_channels)]
+    got_soft = [[] for _ in range(n_channels)]
+    for b in sub:
+        batch.process_device(b.data_ptr(), chunk, chunk)
+        hard, lens, soft = batch.fetch()
+        for c in range(n_channels):
+            got_hard[c].append(hard[c, :lens[c]].copy())
+            got_soft[c].append(soft[c, :lens[c]].copy())
+    flags = batch.error_flags()
+    batch.close()
+    got = [(np.concatenate(h), np.concatenate(s)) for h, s in zip(got_hard, got_soft)]
+    report = {"c2": parity.fast_mode_report(got, shape.create_args, iq, chunk), "error_flags": flags}
+    report["c2"]["signal"] = "%d channels x %d samples (%.2f s each), calls of %d" % (n_channels, iq.shape[1], iq.shape[1] /
+                                                                                  shape.sampling_freq, chunk)
+    golden_dir = os.path.join(ROOT, "tests", "golden")
+    goldens = {"nusat": ("nusat.cf32", (192000, 40000, 5000, 1, 2000, True)),
+               "nan": ("inputnan.cf32", (240000, 9600, 5000, 1, 2000, True)),
+               "lucky7": ("lucky7.expected.cf32", (48000, 4800, 5000, 2, 2000, True)),
+               "lucky7_nodc": ("lucky7.expected.cf32", (48000, 4800, 5000, 2, 2000, False))}
+    reports = []
+    for name, (fname, gargs) in sorted(goldens.items()):
+        path = os.path.join(golden_dir, fname)
+        if not os.path.exists(path):
+            continue
+        x = np.fromfile(path, dtype=np.complex64)[None, :]
+        b = sdrm.FskDemodBatch(1, *gargs, 4096, fast=True, soft=True, device=device)
+        hard, soft = b.run_stream(x, 4096)
+        b.close()
+        r = parity.fast_mode_report([(hard[0], soft[0])], gargs, x, 4096)
+        report["golden_" + name] = r
+        reports.append(r)
+    if reports:
+        merged = parity.merge(reports)
+        merged["channels_bit_identical_to_fma_order_reference"] = sum(
+            r["channels_bit_identical_to_fma_order_reference"] or 0 for r in reports)
+        report["goldens_all"] = merged
+    return report
+
+
+def run_other_configs(args, world, rank, local_rank, fp32_peak):
+    """BASELINE.json configs other than the headline one, each as {name, value, unit, ms_per_step, roofline_frac, ...}.
+    N = 1: configs[3] (modulator, 1024 channels and at the channel count where the phase walkers fill the GPU), a 256-channel
+    subset of configs[2] (Doppler + 2.4 Msps chain; the full 4096 channels take 0.6 s per step) and configs[0] (one CPU channel).
+    N = 8: configs[4], 32768 channels = 4096 per GPU."""
+    import bench_configs
+    out = []
+
+    class A:
+        pass
+
+    if world == 1:
+        for n_ch, name in ((1024, "configs[3] gfsk_mod 1024 channels"), (16384, "configs[3] shape at 16384 channels (walkers saturated)")):
+            a = A()
+            a.channels, a.steps, a.warmup, a.device, a.no_cpu = n_ch, 50 if n_ch == 1024 else 10, 3, local_rank, args.no_cpu or n_ch != 1024
+            try:
+                r = bench_configs.bench_c4(a)
+                out.append({"name": name, "metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
+                            "steps": a.steps, "roofline_bound": "hbm", "roofline_achieved_gbs": r["roofline"]["achieved"],
+                            "roofline_peak_gbs": r["roofline"]["peak"], "roofline_frac": r["roofline"]["frac"],
+                            "cpu_value": r["cpu_baseline"]["value"] if r["cpu_baseline"] else None,
+                            "cpu_cores": r["cpu_baseline"]["cores"] if r["cpu_baseline"] else None,
+                            "gpu_launches": r["gpu_launches"], "note": r["roofline"]["note"]})
+            except Exception as e:  # a secondary line must not cost the headline
+                out.append({"name": name, "error": repr(e)[:200]})
+        a = A()
+        a.channels, a.steps, a.warmup, a.device, a.no_cpu, a.mode, a.fp32_peak = 256, 2, 3, local_rank, args.no_cpu, "exact", fp32_peak
+        try:
+            r = bench_configs.bench_c3(a)
+            out.append({"name": "configs[2] doppler + GMSK 2400 baud from 2.4 Msps, 256-channel subset of the 4096", "metric": r["metric"],
+                        "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"], "steps": a.steps,
+                        "roofline_bound": "fp32", "roofline_achieved_tflops": r["roofline"]["achieved"],
+                        "roofline_peak_tflops": r["roofline"]["peak"], "roofline_frac": r["roofline"]["frac"],
+                        "kernel_ms": r["roofline"]["kernel_ms"], "kernel_frac": r["roofline"]["kernel_frac"],
+                        "flop_per_sample": r["config"]["flop_per_sample"],
+                        "cpu_value": r["cpu_baseline"]["value"] if r["cpu_baseline"] else None,
+                        "cpu_cores": r["cpu_baseline"]["cores"] if r["cpu_baseline"] else None,
+                        "error_flags": r["error_flags"], "workload": r["config"]["workload"]})
+        except Exception as e:
+            out.append({"name": "configs[2]", "error": repr(e)[:200]})
+        if not args.no_cpu:
+            try:
+                r = bench_configs.bench_c1(a)
+                out.append({"name": "configs[0] one channel on one host core (reference CPU chain, strict build)", "metric": r["metric"],
+                            "value": r["value"], "unit": r["unit"], "cpu_cores": 1,
+                            "perf_fsk_modem_shape_value": r["shapes"]["perf_fsk_modem_48k_4800"]["msamples_per_s"],
+                            "seconds": r["shapes"]["c1_192k_9600"]["seconds"]})
+            except Exception as e:
+                out.append({"name": "configs[0]", "error": repr(e)[:200]})
+    return out
+
+
+def run_c5(args, world, rank, local_rank, device, shape, fp32_peak, dist):
+    """BASELINE configs[4]: 32768 channels of the headline shape, 4096 per GPU on 8 GPUs (every rank takes part)."""
+    import torch
+    import sdrm
+    import workloads
+    n_ch, chunk, steps = 4096, args.chunk, 5
+    cap = int(chunk / 20 * 1.1) + 64
+    batch = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=cap, device=local_rank)
+    bufs = []
+    for i in range(2):
+        x = workloads.gfsk_channels(n_ch, chunk, shape, seed=1000 + rank * n_ch + 7919 * i, device=device)
+        bufs.append(x)
+    pin_out = sdrm.PinnedArray((n_ch, cap), np.int8, device=local_rank)
+    pin_len = sdrm.PinnedArray((n_ch,), np.uint32, device=local_rank)
+    fir = torch.cuda.ExternalStream(batch.stream, device=device)
+    out = torch.cuda.ExternalStream(batch.out_stream, device=device)
+
+    def loop(n):
+        fetched = 0
+        for k in range(n):
+            batch.process_device(bufs[k % 2].data_ptr(), chunk, chunk)
+            if k + 1 >= 3:
+                batch.fetch_ptr(pin_out.ptr, cap, pin_len.ptr)
+                fetched += 1
+        while fetched < n:
+            batch.fetch_ptr(pin_out.ptr, cap, pin_len.ptr)
+            fetched += 1
+
+    loop(3)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(fir)
+    loop(steps)
+    e1.record(out)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    flags = batch.error_flags()
+    batch.close()
+    pin_out.close()
+    pin_len.close()
+    flops, _, _ = workloads.demod_flops_per_sample(shape)
+    value = world * n_ch * chunk / (ms * 1e-3) / 1e6
+    return {"name": "configs[4] 32768 channels of the headline shape, 4096 per GPU x %d GPUs" % world, "metric": METRIC, "value": value,
+            "unit": UNIT, "ms_per_step": ms, "steps": steps, "channels_total": world * n_ch, "roofline_bound": "fp32",
+            "roofline_frac": value / world * 1e6 * flops / 1e12 / fp32_peak, "error_flags": flags}
 
 
 def main():
     args = parse_args()
     claim_stdout()
     import workloads
-    shape = workloads.DemodShape("gmsk9600@192k/chunk%d" % args.chunk, 192000, 9600, 5000, 2, 2000, True, args.chunk)
+    shape = c2_shape(args.chunk)
     if args.impl == "reference":
         run_reference_arm(args, shape)
         return
@@ -228,12 +429,35 @@ def main():
     # host threads and the pinned buffers they allocate stay on the socket of this rank's GPU
     all_cpus = os.sched_getaffinity(0)
     local_cpus = sdrm.bind_thread_near_device(local_rank)
+    numa_node = sdrm.lib.sdrm_device_numa_node(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # the FP32 pipe of this device, measured now with the FIR kernels' own instruction mixes (roofline denominator)
+    fma_peak, pair_peak = sdrm.measure_fp32_peak(local_rank)
 
     n_ch, chunk = args.channels, args.chunk
     first_channel = rank * n_ch  # channel c of the job is the same signal on any sharding
     cap = int(chunk / shape.decimation / (shape.sampling_freq / shape.baud_rate / shape.decimation) * 1.1) + 64
     batch = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=cap, fast=(args.mode == "fast"),
-                               device=local_rank, debug_flags=(0x80000000 if args.debug_no_tail else 0))
+                               device=local_rank, measurement_aid=(sdrm.AID_NO_TAIL if args.debug_no_tail else 0))
 
     # two resident input buffers of 8 * n_ch * chunk bytes each (1 GiB at the defaults) >> 126 MB L2
     n_buf = 2
@@ -245,21 +469,27 @@ def main():
     gen_s = time.time() - t0
 
     fir_stream = torch.cuda.ExternalStream(batch.stream, device=device)
-    tail_stream = torch.cuda.ExternalStream(batch.tail_stream, device=device)
+    out_stream = torch.cuda.ExternalStream(batch.out_stream, device=device)
+    pin_out = [sdrm.PinnedArray((n_ch, cap), np.int8, device=local_rank) for _ in range(2)]
+    pin_len = [sdrm.PinnedArray((n_ch,), np.uint32, device=local_rank) for _ in range(2)]
+    depth = 3  # SDRM_MAX_IN_FLIGHT
 
-    def step(k):
-        batch.process_device(bufs[k % n_buf].data_ptr(), chunk, chunk)
-        batch.release()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def device_loop(b, n_steps, first=0):
+        """n_steps calls on resident input, results (int8 symbols + counts) fetched into pinned host memory: the serial tail of
+        call k and the result copy of call k - 1 run under the filters of call k + 1"""
+        fetched = 0
+        for k in range(n_steps):
+            b.process_device(bufs[(first + k) % n_buf].data_ptr(), chunk, chunk)
+            if k + 1 >= depth:
+                b.fetch_ptr(pin_out[fetched % 2].ptr, cap, pin_len[fetched % 2].ptr)
+                fetched += 1
+        while fetched < n_steps:
+            b.fetch_ptr(pin_out[fetched % 2].ptr, cap, pin_len[fetched % 2].ptr)
+            fetched += 1
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for k in range(args.warmup):
-        step(k)
+    device_loop(batch, args.warmup)
     sampler.wait_first_sample()
     barrier()
     launches_before = batch.launch_count
@@ -267,50 +497,43 @@ def main():
     end = torch.cuda.Event(enable_timing=True)
     t_begin = time.time()
     start.record(fir_stream)
-    for k in range(args.steps):
-        step(args.warmup + k)
-    end.record(tail_stream)
+    device_loop(batch, args.steps, first=args.warmup)
+    end.record(out_stream)  # the last fetch has returned: every kernel and result copy of the K steps is done
     barrier()
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end)
-    ms_total = start.elapsed_time(end)
+    ms_total = max_over_ranks(start.elapsed_time(end))
     launches = int(batch.launch_count - launches_before)
+    symbols_last = int(pin_len[0].array.sum())
 
     # per-kernel times of the dominant kernel, CUDA events on its own stream, inside a (second) timed loop
     batch.set_profiling(True)
     k1_ms, k3_ms, tail_ms, call_ms = [], [], [], []
     for k in range(min(args.steps, 5)):
-        step(k)
+        batch.process_device(bufs[k % n_buf].data_ptr(), chunk, chunk)
+        batch.release()
         t = batch.stage_times()
         k1_ms.append(t[0]); k3_ms.append(t[1]); tail_ms.append(t[2]); call_ms.append(t[3])
     batch.set_profiling(False)
     flags = batch.error_flags()
 
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     samples_per_step = world * n_ch * chunk
     value = samples_per_step * args.steps / (ms_total * 1e-3) / 1e6
 
-    # ---- the same workload in the optional FMA arithmetic (one FFMA2 per tap, not the parity-defining mode): shows what the
-    # kernels reach once the bit-exact multiply-then-add no longer halves the pipe's useful rate -------------------------------
+    # ---- the same workload in the optional FMA arithmetic (one FFMA2 per tap, not the parity-defining mode) -----------------
     fma_mode = None
+    parity_report = None
     if args.mode == "exact" and world == 1 and not args.no_fma_line:
         fast = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=cap, fast=True, device=local_rank)
         fast_fir = torch.cuda.ExternalStream(fast.stream, device=device)
-        fast_tail = torch.cuda.ExternalStream(fast.tail_stream, device=device)
+        fast_out = torch.cuda.ExternalStream(fast.out_stream, device=device)
         fast_steps = max(3, min(args.steps, 20))
-        for k in range(max(3, args.warmup)):
-            fast.process_device(bufs[k % n_buf].data_ptr(), chunk, chunk)
-            fast.release()
+        device_loop(fast, max(3, args.warmup))
         torch.cuda.synchronize()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(fast_fir)
-        for k in range(fast_steps):
-            fast.process_device(bufs[k % n_buf].data_ptr(), chunk, chunk)
-            fast.release()
-        f1.record(fast_tail)
+        device_loop(fast, fast_steps)
+        f1.record(fast_out)
         torch.cuda.synchronize()
         fast_ms = f0.elapsed_time(f1) / fast_steps
         fast.set_profiling(True)
@@ -319,25 +542,23 @@ def main():
             fast.process_device(bufs[k % n_buf].data_ptr(), chunk, chunk)
             fast.release()
             fast_k1.append(fast.stage_times()[0])
-        fma_mode = {"value": n_ch * chunk / (fast_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": fast_ms, "steps": fast_steps,
-                    "kernel_ms": float(np.mean(fast_k1)), "error_flags": fast.error_flags(),
-                    "note": "SDRM_FLAG_FAST_FMA: same summation order, fused rounding; bit-identical to the FMA-order build of the "
-                            "reference, not to its strict build"}
+        fma_mode = {"value": n_ch * chunk / (fast_ms * 1e-3) / 1e6, "ms_per_step": fast_ms, "steps": fast_steps,
+                    "kernel_ms": float(np.mean(fast_k1)), "error_flags": fast.error_flags()}
         fast.close()
+        if not args.no_parity and not args.no_cpu:
+            parity_report = fast_mode_parity(sdrm, shape, bufs, min(64, n_ch), cap, local_rank)
 
     # ---- end to end through the host-buffer entry points (pinned input, H2D + D2H in the timed region) ----------
     e2e = None
     if not args.no_e2e:
         e2e_steps = max(3, min(args.steps, 12))
-        pin_in = [sdrm.PinnedArray((n_ch, chunk), np.complex64) for _ in range(2)]
-        pin_out = [sdrm.PinnedArray((n_ch, cap), np.int8) for _ in range(2)]
-        pin_len = [sdrm.PinnedArray((n_ch,), np.uint32) for _ in range(2)]
+        pin_in = [sdrm.PinnedArray((n_ch, chunk), np.complex64, device=local_rank) for _ in range(2)]
         for i in range(2):
             torch.from_numpy(pin_in[i].array.view(np.float32).reshape(n_ch, 2 * chunk)).copy_(
                 torch.view_as_real(bufs[i]).reshape(n_ch, 2 * chunk))
         torch.cuda.synchronize()
 
-        def pipelined(submit, n_steps, depth=3):
+        def pipelined(submit, n_steps):
             """keep `depth` calls in flight (SDRM_MAX_IN_FLIGHT): the copy of call k+2 runs under the filters of call k+1"""
             fetched = 0
             for k in range(n_steps):
@@ -349,99 +570,158 @@ def main():
                 batch.fetch_ptr(pin_out[fetched % 2].ptr, cap, pin_len[fetched % 2].ptr)
                 fetched += 1
 
-        def e2e_loop(n_steps):
-            pipelined(lambda k: batch.submit_ptr(pin_in[k % 2].ptr, chunk, chunk), n_steps)
+        def timed(loop):
+            loop(3)
+            barrier()
+            t_start = time.perf_counter()
+            loop(e2e_steps)
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t_start)
 
-        e2e_loop(3)
-        barrier()
-        t_start = time.perf_counter()
-        e2e_loop(e2e_steps)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t_start
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s = timed(lambda n: pipelined(lambda k: batch.submit_ptr(pin_in[k % 2].ptr, chunk, chunk), n))
         symbols = int(pin_len[0].array.sum())
-        e2e = {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": UNIT,
+        # what the platform gives these N GPUs at once for the same buffers: plain pinned copies, nothing else running
+        scratch = torch.empty(n_ch * chunk, dtype=torch.complex64, device=device)
+        sdrm.probe_h2d(local_rank, pin_in[0].ptr, scratch.data_ptr(), n_ch * chunk * 8, 2)
+        barrier()
+        probe_reps = 6
+        probe_s = sdrm.probe_h2d(local_rank, pin_in[0].ptr, scratch.data_ptr(), n_ch * chunk * 8, probe_reps)
+        my_gbs = n_ch * chunk * 8 * probe_reps / probe_s / 1e9
+        ceiling_gbs = world * n_ch * chunk * 8 * probe_reps / max_over_ranks(probe_s) / 1e9
+        sum_gbs = sum_over_ranks(my_gbs)
+        del scratch
+        e2e_value = samples_per_step * e2e_steps / e2e_s / 1e6
+        e2e = {"value": e2e_value, "unit": UNIT,
                "h2d_bytes_per_step": world * n_ch * chunk * 8, "d2h_bytes_per_step": world * (n_ch * cap + n_ch * 4),
-               "steps": e2e_steps, "symbols_last_step": symbols}
+               "steps": e2e_steps, "symbols_last_step": symbols,
+               "h2d_gbs": e2e_value * 8e6 / 1e9,
+               "h2d_ceiling_gbs": ceiling_gbs, "h2d_ceiling_sum_of_ranks_gbs": sum_gbs,
+               "frac_of_ceiling": e2e_value * 8e6 / 1e9 / ceiling_gbs,
+               "h2d_ceiling_how": "plain cudaMemcpyAsync of the same pinned buffers (%d x %.2f GiB per rank), all %d ranks at once, "
+                                  "no kernels; total bytes / slowest rank" % (probe_reps, n_ch * chunk * 8 / 2 ** 30, world),
+               "pinned_numa_node": numa_node}
         # the same stream as 12-bit int16 IQ (what the PlutoSDR hands over, plutosdr.c:129), converted on the device:
         # half the host->device bytes. Reported beside the cf32 figure, which stays the headline (the reference API is cf32).
-        pin_in16 = [sdrm.PinnedArray((n_ch, chunk, 2), np.int16) for _ in range(2)]
+        pin_in16 = [sdrm.PinnedArray((n_ch, chunk, 2), np.int16, device=local_rank) for _ in range(2)]
         for i in range(2):
             q = torch.clamp(torch.round(torch.view_as_real(bufs[i]) * 1500.0), -2048, 2047).to(torch.int16)
             torch.from_numpy(pin_in16[i].array).copy_(q)
         torch.cuda.synchronize()
-
-        def e2e16_loop(n_steps):
-            pipelined(lambda k: batch.submit_i16_ptr(pin_in16[k % 2].ptr, chunk, chunk), n_steps)
-
-        e2e16_loop(3)
-        barrier()
-        t_start = time.perf_counter()
-        e2e16_loop(e2e_steps)
-        torch.cuda.synchronize()
-        e2e16_s = time.perf_counter() - t_start
-        if world > 1:
-            t = torch.tensor([e2e16_s], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e16_s = float(t.item())
-        e2e["int16_ingest"] = {"value": samples_per_step * e2e_steps / e2e16_s / 1e6, "unit": UNIT,
-                               "h2d_bytes_per_step": world * n_ch * chunk * 4, "symbols_last_step": int(pin_len[0].array.sum())}
-        for a in pin_in + pin_out + pin_len + pin_in16:
+        e2e16_s = timed(lambda n: pipelined(lambda k: batch.submit_i16_ptr(pin_in16[k % 2].ptr, chunk, chunk), n))
+        e2e16_value = samples_per_step * e2e_steps / e2e16_s / 1e6
+        e2e["int16_value"] = e2e16_value
+        e2e["int16_h2d_bytes_per_step"] = world * n_ch * chunk * 4
+        e2e["int16_frac_of_ceiling"] = e2e16_value * 4e6 / 1e9 / ceiling_gbs
+        e2e["int16_symbols_last_step"] = int(pin_len[0].array.sum())
+        for a in pin_in + pin_in16:
             a.close()
+    flags |= batch.error_flags()
+    batch.close()
+    del bufs
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4] on 8 GPUs (all ranks), the other configs on rank 0 at N = 1 ----------------------------------------
+    configs = []
+    if not args.no_configs and world == 8:
+        c5 = run_c5(args, world, rank, local_rank, device, shape, fma_peak, dist)
+        configs.append(c5)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    if not args.no_configs and world == 1:
+        os.sched_setaffinity(0, all_cpus)
+        configs += run_other_configs(args, world, rank, local_rank, fma_peak)
+
     peaks, peaks_kind = measured_peaks()
     flops_per_sample, t1, t2 = workloads.demod_flops_per_sample(shape)
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-    fp32_peak_tflops = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    nominal_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     k1 = float(np.mean(k1_ms))
     k1_flops = 4.0 * t1 * n_ch * chunk  # 2 mul + 2 add per tap per complex sample
     achieved = k1_flops / (k1 * 1e-3) / 1e12
     in_bytes = 8.0 * n_ch * chunk
+    step_ms = ms_total / args.steps
     roofline = {
         "bound": "fp32",
         "kernel": "fir_tile_kernel<1> (lpf1 + quadrature demod)",
-        "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
-        "peak_source": "148 SMs x 128 FP32 lanes x 2 flop x %.0f MHz (sm_max_mhz, %s); FMA peak — exact mode issues a separately "
-                       "rounded multiply and add per tap, so its own ceiling is 0.5" % (sm_max, peaks_kind),
-        "pipe_frac": achieved / fp32_peak_tflops * (2.0 if args.mode == "exact" else 1.0),
-        "kernel_ms": k1, "kernel_share_of_step": k1 / (ms_total / args.steps),
+        "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
+        "peak_source": "measured",
+        "peak_how": "sdrm_measure_fp32_peak on this device at start: FFMA2 stream, best of 5; nominal 148 SMs x 128 lanes x 2 x "
+                    "%.0f MHz = %.2f" % (sm_max, nominal_peak),
+        "peak_nominal": nominal_peak,
+        "exact_mode_ceiling": pair_peak,
+        "frac_of_exact_mode_ceiling": achieved / pair_peak if args.mode == "exact" else None,
+        "exact_mode_ceiling_how": "same microbenchmark with the separately rounded multiply and add of exact mode (two FFMA2 per "
+                                  "tap): what bit-exact arithmetic allows on this pipe",
+        "chain_achieved": value / world * 1e6 * flops_per_sample / 1e12,
+        "chain_frac": value / world * 1e6 * flops_per_sample / 1e12 / fma_peak,
+        "kernel_ms": k1, "kernel_share_of_step": k1 / step_ms,
         "traffic": k1_traffic(n_ch * chunk),
-        "hbm": {"achieved": (in_bytes + in_bytes / 2) / (k1 * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s"},
-        "fma_mode": None if fma_mode is None else dict(
-            fma_mode, achieved=k1_flops / (fma_mode["kernel_ms"] * 1e-3) / 1e12,
-            frac=k1_flops / (fma_mode["kernel_ms"] * 1e-3) / 1e12 / fp32_peak_tflops),
-        "stage_ms": {"lpf1_quad": k1, "lpf2": float(np.mean(k3_ms)), "dc_clock_tail": float(np.mean(tail_ms)),
-                     "call_unpipelined": float(np.mean(call_ms))},
+        "algorithmic_bytes": in_bytes + in_bytes / 2,
+        "hbm_achieved_gbs": (in_bytes + in_bytes / 2) / (k1 * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
+        "lpf1_quad_ms": k1, "lpf2_ms": float(np.mean(k3_ms)), "dc_clock_tail_ms": float(np.mean(tail_ms)),
+        "call_unpipelined_ms": float(np.mean(call_ms)),
     }
+    if fma_mode is not None:
+        fa = k1_flops / (fma_mode["kernel_ms"] * 1e-3) / 1e12
+        roofline.update({
+            "fma_note": "SDRM_FLAG_FAST_FMA (one FFMA2 per tap, same summation order): bit-identical to the FMA-order build of the "
+                        "reference, NOT parity-defining; fma_parity_* count its deviation from the strict reference build",
+            "fma_value": fma_mode["value"], "fma_ms_per_step": fma_mode["ms_per_step"], "fma_kernel_ms": fma_mode["kernel_ms"],
+            "fma_achieved": fa, "fma_frac": fa / fma_peak, "fma_error_flags": fma_mode["error_flags"]})
+        if parity_report is not None:
+            c2 = parity_report["c2"]
+            g = parity_report.get("goldens_all")
+            roofline.update({
+                "fma_parity_rule": c2["rule"],
+                "fma_parity_c2_signal": c2["signal"],
+                "fma_parity_c2_symbols": c2["symbols"],
+                "fma_parity_c2_soft_over_1e-4": c2["soft_rel_over_1e-4"],
+                "fma_parity_c2_soft_over_1e-4_strong": c2["soft_rel_over_1e-4_strong"],
+                "fma_parity_c2_hard_flips": c2["hard_flips"],
+                "fma_parity_c2_hard_flips_strong": c2["hard_flips_strong"],
+                "fma_parity_c2_max_int8_delta": c2["max_int8_delta"],
+                "fma_parity_c2_max_abs_dsoft": c2["max_abs_dsoft"],
+                "fma_parity_c2_channels_bit_identical_to_fma_reference": c2["channels_bit_identical_to_fma_order_reference"],
+                "fma_parity_c2_channels": c2["channels"]})
+            if g is not None:
+                roofline.update({
+                    "fma_parity_goldens_symbols": g["symbols"],
+                    "fma_parity_goldens_soft_over_1e-4_strong": g["soft_rel_over_1e-4_strong"],
+                    "fma_parity_goldens_hard_flips_strong": g["hard_flips_strong"],
+                    "fma_parity_goldens_max_int8_delta": g["max_int8_delta"],
+                    "fma_parity_goldens_bit_identical_to_fma_reference": g["channels_bit_identical_to_fma_order_reference"],
+                    "fma_parity_nodc_hard_flips_strong": parity_report["golden_lucky7_nodc"]["hard_flips_strong"],
+                    "fma_parity_nodc_max_int8_delta": parity_report["golden_lucky7_nodc"]["max_int8_delta"]})
+            roofline["fma_parity"] = parity_report
     cpu = None
     if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
         os.sched_setaffinity(0, all_cpus)  # the reference gets every host core, not only the GPU's socket
-        cpu = cpu_reference_run(shape, args.cpu_seconds)
-        if cpu is not None:
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        from oracle import ref
+        strict = cpu_reference_run(shape, args.cpu_seconds)
+        if strict is not None:
+            cpu = {k: strict[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu["build"] = "strict (parity-defining)"
+            if ref.available("tuned") and ref.tuned_level():
+                tuned = cpu_reference_run(shape, args.cpu_seconds / 2, build="tuned")
+                cpu["tuned_value"] = tuned["value"]
+                cpu["tuned_sample"] = tuned["sample"]
+    config = c2_config(args, shape, args.mode)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%d channels/GPU x %s, GMSK BT 0.5, Eb/N0 12 dB, dev 5 kHz, decim 2, dc on (BASELINE configs[1])"
-                               % (n_ch, shape.name),
-                   "channels_per_gpu": n_ch, "chunk": chunk, "mode": args.mode, "parallelism": "channels sharded, no collective",
-                   "l2": "inputs larger than L2 (2 x %.2f GiB rotating)" % (n_ch * chunk * 8 / 2 ** 30),
-                   "realtime_channels_per_gpu": value / world * 1e6 / shape.sampling_freq,
-                   "flop_per_sample": flops_per_sample, "t1": t1, "t2": t2, "input_gen_s": gen_s,
-                   "host_cpus_near_gpu": local_cpus},
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "error_flags": flags, "lib": sdrm.version(),
+        "value_includes": "int8 symbols + counts copied to pinned host memory every step (%d B per step)" % (n_ch * cap + n_ch * 4),
+        "symbols_last_step": symbols_last,
+        "realtime_channels_per_gpu": value / world * 1e6 / shape.sampling_freq,
+        "input_gen_s": gen_s, "host_cpus_near_gpu": local_cpus,
+        "configs": configs, "error_flags": flags, "lib": sdrm.version(),
     }
-    emit_line(line)
+    emit_line(line, args.full_line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -66,6 +66,14 @@ void sdrm_rx_group_shutdown(sdrm_rx_group *group);
 /* number of blocks fully processed and delivered so far */
 uint64_t sdrm_rx_group_blocks_done(const sdrm_rx_group *group);
 
+/* 1 once the group's thread has stopped on an error (a block that could not be enqueued, a failed result copy):
+ * the reference's worker thread ends in the same situations; 0 while it is healthy */
+int sdrm_rx_group_failed(const sdrm_rx_group *group);
+
+/* sessions whose client socket could not be written to: they are no longer served (the reference's dsp_worker ends
+ * on the first failed write, src/dsp_worker.c:93-103), the other sessions of the group carry on */
+uint32_t sdrm_rx_group_sessions_failed(const sdrm_rx_group *group);
+
 void sdrm_rx_group_destroy(sdrm_rx_group *group);
 
 #endif

@@ -39,10 +39,18 @@ typedef struct {
     bool use_dc_block;
     uint32_t max_input_buffer_length; /* samples per channel per call, as in the reference */
     uint32_t max_symbols_per_call;    /* output capacity per channel; 0 = max_input_buffer_length (reference) */
-    uint32_t flags;
+    uint32_t flags;                   /* SDRM_FLAG_*; unknown bits are rejected with -1 */
     int device;                       /* CUDA device ordinal, -1 = current */
 } sdrm_fsk_demod_batch_config;
 
+/*
+ * Parameter ranges narrower than the reference's fsk_demod_create (the fused serial tail keeps one symbol step plus one
+ * 32-row block of every channel in shared memory); create logs the reason and returns -1 outside them:
+ *   samples per symbol after decimation, sps = sampling_freq / baud_rate / decimation:  1 <= sps <= 900
+ *   with use_dc_block: dc blocker length ceil(32 * sps) >= 32, i.e. sps >= 1 (the reference accepts fractional sps < 1,
+ *   which no FSK receiver can use).
+ * Batches of more than 65535 channels are accepted (kernels that index rows with gridDim.y loop over the remainder).
+ */
 int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_fsk_demod_batch **batch);
 
 /*
@@ -84,9 +92,14 @@ int sdrm_fsk_demod_batch_fetch(sdrm_fsk_demod_batch *batch, int8_t *output, floa
 /* Forgets the oldest un-fetched call without copying its results (device-resident pipelines). */
 int sdrm_fsk_demod_batch_release(sdrm_fsk_demod_batch *batch);
 
-/* Device pointers of the most recently enqueued call's results: int8 [channels][*out_stride], uint32 [channels]. */
+/* Device pointers of the most recently enqueued call's results: int8 [channels][*out_stride], uint32 [channels].
+ * They are complete once the call's tail has run: order the consumer with sdrm_fsk_demod_batch_wait_outputs. The buffers are
+ * reused SDRM_MAX_IN_FLIGHT calls later; a device-resident consumer that releases calls without fetching them must have
+ * its own stream wait (below) before the batch is given the call that reuses the slot. */
 int sdrm_fsk_demod_batch_device_outputs(sdrm_fsk_demod_batch *batch, const int8_t **d_output, const uint32_t **d_output_len,
                                         size_t *out_stride);
+/* Makes `stream` (a cudaStream_t) wait for the tail of the most recently enqueued call. */
+int sdrm_fsk_demod_batch_wait_outputs(sdrm_fsk_demod_batch *batch, void *stream);
 
 /* Blocks until everything enqueued so far has finished. */
 int sdrm_fsk_demod_batch_sync(sdrm_fsk_demod_batch *batch);
@@ -95,6 +108,8 @@ int sdrm_fsk_demod_batch_sync(sdrm_fsk_demod_batch *batch);
 void *sdrm_fsk_demod_batch_stream(sdrm_fsk_demod_batch *batch);
 /* cudaStream_t of the serial tail (dc blocker, clock recovery). */
 void *sdrm_fsk_demod_batch_tail_stream(sdrm_fsk_demod_batch *batch);
+/* cudaStream_t the result copies of sdrm_fsk_demod_batch_fetch are issued on. */
+void *sdrm_fsk_demod_batch_out_stream(sdrm_fsk_demod_batch *batch);
 
 /* Number of kernels launched by this batch since creation (bench.py reports it as gpu_launches). */
 uint64_t sdrm_fsk_demod_batch_launch_count(const sdrm_fsk_demod_batch *batch);
@@ -222,7 +237,13 @@ int sdrm_samples_cf32_to_i16_device(const void *d_input, size_t in_stride, void 
 
 /* Pinned host memory for the host-buffer entry points (pageable memory works too, but copies serialise). */
 void *sdrm_pinned_alloc(size_t bytes);
+/* The same on the NUMA node of CUDA device `device`: anonymous 2 MB-aligned mapping bound to the node the kernel reports for
+ * the device's PCI function (/sys/bus/pci/devices/<id>/numa_node), transparent huge pages requested, registered with the
+ * driver. Where no node is reported (-1: single-node hosts, most virtual machines) it is sdrm_pinned_alloc. */
+void *sdrm_pinned_alloc_near_device(size_t bytes, int device);
 void sdrm_pinned_free(void *p);
+/* NUMA node of a CUDA device's PCI function, -1 when the platform does not say. */
+int sdrm_device_numa_node(int device);
 
 /*
  * Moves the calling thread onto the CPUs that are local to CUDA device `device` (sysfs local_cpulist of its PCI function,
@@ -233,6 +254,20 @@ void sdrm_pinned_free(void *p);
 int sdrm_bind_thread_near_device(int device);
 /* Parser behind it, exported for tests: number of CPUs in a sysfs cpu list such as "0-23,48-71", -1 if malformed. */
 int sdrm_cpulist_parse_count(const char *text);
+
+/*
+ * Measures the FP32 pipe of `device` (-1 = current) with the two instruction mixes of the FIR kernels, in algorithmic TFLOP/s
+ * (multiply + add = 2 flop per float lane and tap): *fma_tflops one FFMA2 per tap (the FMA peak roofline fractions are quoted
+ * against), *exact_pair_tflops the separately rounded multiply and add of exact mode (two FFMA2 per tap). Synchronous, ~15 ms.
+ */
+int sdrm_measure_fp32_peak(int device, double *fma_tflops, double *exact_pair_tflops);
+
+/*
+ * Times `repeats` plain cudaMemcpyAsync copies of `bytes` from `host` (pinned) to `d_scratch` on a stream of its own and
+ * returns the elapsed device time in *seconds: the platform's host -> device ceiling for that buffer at that moment (run it
+ * on all GPUs at once to see what the host gives N of them together).
+ */
+int sdrm_probe_h2d(int device, const void *host, void *d_scratch, size_t bytes, int repeats, double *seconds);
 
 /* Library/runtime identification: "sdr-modem_b200 <version>; sm_100a; CUDA runtime <n>". */
 const char *sdrm_version(void);

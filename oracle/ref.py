@@ -15,7 +15,27 @@ _LIBS = {}
 c_float_p = C.POINTER(C.c_float)
 
 
+def tuned_level():
+    """x86-64 micro-architecture level of the tuned CPU build this machine can run: 4 (AVX-512), 3 (AVX2 + FMA) or 0."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = set()
+            for line in f:
+                if line.startswith("flags"):
+                    flags = set(line.split(":", 1)[1].split())
+                    break
+    except OSError:
+        return 0
+    if {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags:
+        return 4
+    if {"avx2", "fma", "bmi2", "movbe"} <= flags:
+        return 3
+    return 0
+
+
 def lib_path(fma=False):
+    if fma == "tuned":
+        return os.path.join(_HERE, "_ref", "libsdrmodem_ref_tuned_v%d.so" % tuned_level())
     return os.path.join(_HERE, "_ref", "libsdrmodem_ref_fma.so" if fma else "libsdrmodem_ref.so")
 
 
@@ -24,7 +44,9 @@ def available(fma=False):
 
 
 def load(fma=False):
-    key = bool(fma)
+    """fma: False = strict build (the parity-defining checker), True = FMA-order build (checker of fast mode),
+    "tuned" = -O3 vectorised build (CPU baseline only, never a checker)."""
+    key = fma if fma == "tuned" else bool(fma)
     if key in _LIBS:
         return _LIBS[key]
     lib = C.CDLL(lib_path(fma), mode=os.RTLD_LOCAL | os.RTLD_NOW)

@@ -19,6 +19,12 @@
  * With -DSDRM_SHIM_FMA the three dot products accumulate with fmaf() instead (same order).
  * That models the reference on FMA-contracting platforms and is the checker for the
  * library's optional "fast" arithmetic mode; it is NOT the parity-defining oracle.
+ *
+ * With -DSDRM_SHIM_SIMD the dot products keep 16 lane-partial sums that are added up at the
+ * end, the structure of VOLK's SIMD kernels (e.g. volk_32fc_32f_dot_prod_32fc_a_avx: products
+ * accumulated per vector lane, horizontal sum last), so that the compiler vectorises them.
+ * A different summation order, hence different bits: used ONLY for the "tuned" CPU throughput
+ * figure that bench.py reports beside the strict one, never as a checker.
  */
 #ifndef SDRM_ORACLE_VOLK_SHIM_H
 #define SDRM_ORACLE_VOLK_SHIM_H
@@ -52,6 +58,25 @@ static inline void volk_free(void *p) { free(p); }
 #define SDRM_SHIM_MAC(acc, a, b) ((acc) += (a) * (b))
 #endif
 
+#ifdef SDRM_SHIM_SIMD
+static inline void volk_32f_x2_dot_prod_32f_u(float *result, const float *input, const float *taps, unsigned int num_points) {
+    float lane[16] = {0};
+    unsigned int i = 0;
+    for (; i + 16 <= num_points; i += 16) {
+        for (int k = 0; k < 16; k++) {
+            lane[k] += input[i + k] * taps[i + k];
+        }
+    }
+    float acc = 0.0f;
+    for (; i < num_points; i++) {
+        acc += input[i] * taps[i];
+    }
+    for (int k = 0; k < 16; k++) {
+        acc += lane[k];
+    }
+    *result = acc;
+}
+#else
 static inline void volk_32f_x2_dot_prod_32f_u(float *result, const float *input, const float *taps, unsigned int num_points) {
     float acc = 0.0f;
     for (unsigned int i = 0; i < num_points; i++) {
@@ -59,11 +84,43 @@ static inline void volk_32f_x2_dot_prod_32f_u(float *result, const float *input,
     }
     *result = acc;
 }
+#endif
 
 static inline void volk_32f_x2_dot_prod_32f_a(float *result, const float *input, const float *taps, unsigned int num_points) {
     volk_32f_x2_dot_prod_32f_u(result, input, taps, num_points);
 }
 
+#ifdef SDRM_SHIM_SIMD
+typedef float sdrm_v8f __attribute__((vector_size(32), aligned(4)));
+typedef int sdrm_v8i __attribute__((vector_size(32)));
+static inline void volk_32fc_32f_dot_prod_32fc_u(lv_32fc_t *result, const lv_32fc_t *input, const float *taps, unsigned int num_points) {
+    const float *in = (const float *) input;
+    sdrm_v8f acc0 = {0};
+    sdrm_v8f acc1 = {0}; /* lanes: (re, im) of 4 consecutive samples each */
+    const sdrm_v8i lo = {0, 0, 1, 1, 2, 2, 3, 3};
+    const sdrm_v8i hi = {4, 4, 5, 5, 6, 6, 7, 7};
+    unsigned int i = 0;
+    for (; i + 8 <= num_points; i += 8) {
+        const sdrm_v8f t = *(const sdrm_v8f *) (taps + i);
+        acc0 += *(const sdrm_v8f *) (in + 2 * i) * __builtin_shuffle(t, lo);
+        acc1 += *(const sdrm_v8f *) (in + 2 * i + 8) * __builtin_shuffle(t, hi);
+    }
+    float re = 0.0f;
+    float im = 0.0f;
+    for (; i < num_points; i++) {
+        re += in[2 * i] * taps[i];
+        im += in[2 * i + 1] * taps[i];
+    }
+    acc0 += acc1;
+    for (int k = 0; k < 8; k += 2) {
+        re += acc0[k];
+        im += acc0[k + 1];
+    }
+    float *out = (float *) result;
+    out[0] = re;
+    out[1] = im;
+}
+#else
 static inline void volk_32fc_32f_dot_prod_32fc_u(lv_32fc_t *result, const lv_32fc_t *input, const float *taps, unsigned int num_points) {
     const float *in = (const float *) input;
     float re = 0.0f;
@@ -76,6 +133,7 @@ static inline void volk_32fc_32f_dot_prod_32fc_u(lv_32fc_t *result, const lv_32f
     out[0] = re;
     out[1] = im;
 }
+#endif
 
 static inline void volk_32fc_x2_multiply_conjugate_32fc(lv_32fc_t *c, const lv_32fc_t *a, const lv_32fc_t *b, unsigned int num_points) {
     for (unsigned int i = 0; i < num_points; i++) {

@@ -14,12 +14,14 @@ namespace {
 // in: int16 (I, Q) pairs, row r at in + r * in_stride pairs; out: float2 rows. One thread per complex sample: the 4-byte
 // loads and 8-byte stores of a warp are contiguous.
 __global__ void i16_to_cf32_kernel(const short2 *__restrict__ in, size_t in_stride, float2 *__restrict__ out, size_t out_stride,
-                                   float scalar, int n) {
-    const short2 *x = in + (size_t) blockIdx.y * in_stride;
-    float2 *y = out + (size_t) blockIdx.y * out_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const short2 v = x[i];
-        y[i] = make_float2(__fdiv_rn((float) v.x, scalar), __fdiv_rn((float) v.y, scalar));
+                                   float scalar, int n, int rows) {
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+        const short2 *x = in + (size_t) row * in_stride;
+        float2 *y = out + (size_t) row * out_stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const short2 v = x[i];
+            y[i] = make_float2(__fdiv_rn((float) v.x, scalar), __fdiv_rn((float) v.y, scalar));
+        }
     }
 }
 
@@ -33,12 +35,14 @@ __device__ __forceinline__ short to_i16(float v, float scalar) {
 }
 
 __global__ void cf32_to_i16_kernel(const float2 *__restrict__ in, size_t in_stride, short2 *__restrict__ out, size_t out_stride,
-                                   float scalar, int n) {
-    const float2 *x = in + (size_t) blockIdx.y * in_stride;
-    short2 *y = out + (size_t) blockIdx.y * out_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float2 v = x[i];
-        y[i] = make_short2(to_i16(v.x, scalar), to_i16(v.y, scalar));
+                                   float scalar, int n, int rows) {
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+        const float2 *x = in + (size_t) row * in_stride;
+        short2 *y = out + (size_t) row * out_stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const float2 v = x[i];
+            y[i] = make_short2(to_i16(v.x, scalar), to_i16(v.y, scalar));
+        }
     }
 }
 
@@ -48,7 +52,8 @@ dim3 convert_grid(int n, int rows) {
     if (bx > want) {
         bx = want;
     }
-    return dim3((unsigned) bx, (unsigned) rows);
+    // gridDim.y is limited to 65535: larger batches loop over their rows inside the kernel
+    return dim3((unsigned) bx, (unsigned) (rows < 65535 ? rows : 65535));
 }
 
 }  // namespace
@@ -62,7 +67,7 @@ extern "C" int sdrm_cu_i16_to_cf32(const void *in, size_t in_stride, void *out, 
         return -22;
     }
     i16_to_cf32_kernel<<<convert_grid(n, rows), 256, 0, (cudaStream_t) stream>>>((const short2 *) in, in_stride, (float2 *) out,
-                                                                                out_stride, scalar, n);
+                                                                                out_stride, scalar, n, rows);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }
@@ -76,7 +81,7 @@ extern "C" int sdrm_cu_cf32_to_i16(const void *in, size_t in_stride, void *out, 
         return -22;
     }
     cf32_to_i16_kernel<<<convert_grid(n, rows), 256, 0, (cudaStream_t) stream>>>((const float2 *) in, in_stride, (short2 *) out,
-                                                                                out_stride, scalar, n);
+                                                                                out_stride, scalar, n, rows);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }
@@ -88,26 +93,28 @@ namespace {
 
 __global__ void rows_to_pairs_kernel(const float *__restrict__ in, size_t in_stride, float2 *__restrict__ out, size_t out_stride,
                                      int n, int n_ch) {
-    const int p = blockIdx.y;
-    const float *a = in + (size_t) (2 * p) * in_stride;
-    const float *b = 2 * p + 1 < n_ch ? in + (size_t) (2 * p + 1) * in_stride : nullptr;
-    float2 *y = out + (size_t) p * out_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        y[i] = make_float2(a[i], b != nullptr ? b[i] : 0.0f);
+    for (int p = blockIdx.y; 2 * p < n_ch; p += gridDim.y) {
+        const float *a = in + (size_t) (2 * p) * in_stride;
+        const float *b = 2 * p + 1 < n_ch ? in + (size_t) (2 * p + 1) * in_stride : nullptr;
+        float2 *y = out + (size_t) p * out_stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            y[i] = make_float2(a[i], b != nullptr ? b[i] : 0.0f);
+        }
     }
 }
 
 __global__ void pairs_to_rows_kernel(const float2 *__restrict__ in, size_t in_stride, float *__restrict__ out, size_t out_stride,
                                      int n, int n_ch) {
-    const int p = blockIdx.y;
-    const float2 *x = in + (size_t) p * in_stride;
-    float *a = out + (size_t) (2 * p) * out_stride;
-    float *b = 2 * p + 1 < n_ch ? out + (size_t) (2 * p + 1) * out_stride : nullptr;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float2 v = x[i];
-        a[i] = v.x;
-        if (b != nullptr) {
-            b[i] = v.y;
+    for (int p = blockIdx.y; 2 * p < n_ch; p += gridDim.y) {
+        const float2 *x = in + (size_t) p * in_stride;
+        float *a = out + (size_t) (2 * p) * out_stride;
+        float *b = 2 * p + 1 < n_ch ? out + (size_t) (2 * p + 1) * out_stride : nullptr;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const float2 v = x[i];
+            a[i] = v.x;
+            if (b != nullptr) {
+                b[i] = v.y;
+            }
         }
     }
 }

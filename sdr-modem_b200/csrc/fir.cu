@@ -21,6 +21,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "sdrm_cuda.h"
 #include "device_math.cuh"
 
@@ -40,6 +42,8 @@ constexpr int kW2 = kR + 1;               // D=2: sample pairs in the register w
 constexpr int kTapBlock = FIR_TAPBLOCK;   // multiple of kW1 and 2 * kW2 (528 = 44 * 12 = 24 * 22 for 10 outputs per thread)
 static_assert(kTapBlock % kW1 == 0 && kTapBlock % (2 * kW2) == 0 && kR % 2 == 0, "tap block must hold whole window periods");
 constexpr int kSlack = 32;                // float2 of read-ahead slack after each staged sample window
+constexpr int kMaxDevices = 64;           // per-device "function attributes are set" flags
+constexpr int kMaxGridY = 65535;          // kernels that put rows in gridDim.y loop over the rows beyond it
 
 struct FirParams {
     const float2 *in;
@@ -52,6 +56,7 @@ struct FirParams {
     int phase;
     int n_in;
     int n_out;
+    int rows;
     int out_mode;
     void *out;
     size_t out_stride;
@@ -382,25 +387,26 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_
 // of the chain (lpf2 behind a large decimation) or for unusual standalone filters.
 template <bool FAST>
 __global__ void fir_generic_kernel(const FirParams p) {
-    const int row = blockIdx.y;
     const long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= p.n_out) {
         return;
     }
-    const float2 *hist_row = p.hist + (size_t) row * p.hist_len + p.hist_len;
-    const float2 *in_row = p.in + (size_t) row * p.in_stride;
-    long long v = (long long) p.phase + m * p.decimation - (p.n_taps - 1);
-    float2 acc = make_float2(0.0f, 0.0f);
-    for (int j = 0; j < p.n_taps; j++, v++) {
-        float2 x = v < 0 ? hist_row[v] : in_row[v];
-        acc = mac2<FAST>(acc, x, p.taps_dup[j], p.one, p.negzero);
-    }
-    if (p.out_mode == SDRM_FIR_OUT_ROWS) {
-        reinterpret_cast<float2 *>(p.out)[(size_t) row * p.out_stride + m] = acc;
-    } else {
-        size_t ring_row = (size_t) ((p.tc_head + m) & p.tc_mask);
-        *reinterpret_cast<float2 *>(reinterpret_cast<float *>(p.out) + (((size_t) (row >> 4) * (p.tc_mask + 1) + ring_row) << 5) +
-                                    ((2 * row) & 31)) = acc;
+    for (int row = blockIdx.y; row < p.rows; row += gridDim.y) {  // gridDim.y <= 65535
+        const float2 *hist_row = p.hist + (size_t) row * p.hist_len + p.hist_len;
+        const float2 *in_row = p.in + (size_t) row * p.in_stride;
+        long long v = (long long) p.phase + m * p.decimation - (p.n_taps - 1);
+        float2 acc = make_float2(0.0f, 0.0f);
+        for (int j = 0; j < p.n_taps; j++, v++) {
+            float2 x = v < 0 ? hist_row[v] : in_row[v];
+            acc = mac2<FAST>(acc, x, p.taps_dup[j], p.one, p.negzero);
+        }
+        if (p.out_mode == SDRM_FIR_OUT_ROWS) {
+            reinterpret_cast<float2 *>(p.out)[(size_t) row * p.out_stride + m] = acc;
+        } else {
+            size_t ring_row = (size_t) ((p.tc_head + m) & p.tc_mask);
+            *reinterpret_cast<float2 *>(reinterpret_cast<float *>(p.out) + (((size_t) (row >> 4) * (p.tc_mask + 1) + ring_row) << 5) +
+                                        ((2 * row) & 31)) = acc;
+        }
     }
 }
 
@@ -421,72 +427,75 @@ __global__ void __launch_bounds__(kDecOutputs) fir_dec_kernel(const FirParams p,
     float2 *taps_s = dec_smem;                  // n_taps (h, h) pairs
     float2 *span = dec_smem + p.n_taps;         // n_segs segments of seg_len (>= D, odd) samples
     const int D = p.decimation;
-    const int row = blockIdx.y;
     const long long m0 = (long long) blockIdx.x * kDecOutputs;
     const int n_here = (int) min((long long) kDecOutputs, (long long) p.n_out - m0);
-    const float2 *hist_row = p.hist + (size_t) row * p.hist_len + p.hist_len;
-    const float2 *in_row = p.in + (size_t) row * p.in_stride;
     // first input of the span: the oldest sample of output m0
     const long long v0 = (long long) p.phase + m0 * D - (p.n_taps - 1);
     const int span_len = (n_here - 1) * D + p.n_taps;
     for (int i = threadIdx.x; i < p.n_taps; i += kDecOutputs) {
         taps_s[i] = p.taps_dup[i];
     }
-    for (int i = threadIdx.x; i < span_len; i += kDecOutputs) {
-        const long long v = v0 + i;
-        const float2 x = v < 0 ? hist_row[v] : in_row[v];
-        span[(i / D) * seg_len + (i % D)] = x;
-    }
-    __syncthreads();
-    if ((int) threadIdx.x >= n_here) {
-        return;
-    }
-    float2 acc = make_float2(0.0f, 0.0f);
-    const float2 *mine = span + (size_t) threadIdx.x * seg_len;  // sample t * D sits at the start of segment t
-    int jr = 0;                                                  // j mod D
-    const float2 *seg = mine;                                    // segment t + j div D
-#pragma unroll 4
-    for (int j = 0; j < p.n_taps; j++) {
-        acc = mac2<FAST>(acc, seg[jr], taps_s[j], p.one, p.negzero);
-        if (++jr == D) {
-            jr = 0;
-            seg += seg_len;
+    for (int row = blockIdx.y; row < p.rows; row += gridDim.y) {  // gridDim.y <= 65535; one pass for smaller batches
+        const float2 *hist_row = p.hist + (size_t) row * p.hist_len + p.hist_len;
+        const float2 *in_row = p.in + (size_t) row * p.in_stride;
+        for (int i = threadIdx.x; i < span_len; i += kDecOutputs) {
+            const long long v = v0 + i;
+            const float2 x = v < 0 ? hist_row[v] : in_row[v];
+            span[(i / D) * seg_len + (i % D)] = x;
         }
-    }
-    const long long m = m0 + threadIdx.x;
-    if (p.out_mode == SDRM_FIR_OUT_ROWS) {
-        reinterpret_cast<float2 *>(p.out)[(size_t) row * p.out_stride + m] = acc;
-    } else {
-        size_t ring_row = (size_t) ((p.tc_head + m) & p.tc_mask);
-        *reinterpret_cast<float2 *>(reinterpret_cast<float *>(p.out) + (((size_t) (row >> 4) * (p.tc_mask + 1) + ring_row) << 5) +
-                                    ((2 * row) & 31)) = acc;
+        __syncthreads();
+        if ((int) threadIdx.x < n_here) {
+            float2 acc = make_float2(0.0f, 0.0f);
+            const float2 *mine = span + (size_t) threadIdx.x * seg_len;  // sample t * D sits at the start of segment t
+            int jr = 0;                                                  // j mod D
+            const float2 *seg = mine;                                    // segment t + j div D
+#pragma unroll 4
+            for (int j = 0; j < p.n_taps; j++) {
+                acc = mac2<FAST>(acc, seg[jr], taps_s[j], p.one, p.negzero);
+                if (++jr == D) {
+                    jr = 0;
+                    seg += seg_len;
+                }
+            }
+            const long long m = m0 + threadIdx.x;
+            if (p.out_mode == SDRM_FIR_OUT_ROWS) {
+                reinterpret_cast<float2 *>(p.out)[(size_t) row * p.out_stride + m] = acc;
+            } else {
+                size_t ring_row = (size_t) ((p.tc_head + m) & p.tc_mask);
+                *reinterpret_cast<float2 *>(reinterpret_cast<float *>(p.out) + (((size_t) (row >> 4) * (p.tc_mask + 1) + ring_row) << 5) +
+                                            ((2 * row) & 31)) = acc;
+            }
+        }
+        __syncthreads();  // the span is overwritten by the next row
     }
 }
 
 __global__ void hist_update_kernel(const float2 *in, size_t in_stride, const float2 *hist, float2 *hist_next, int hist_len,
-                                   int n_in) {
-    const int row = blockIdx.y;
+                                   int n_in, int rows) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= hist_len) {
         return;
     }
-    long long v = (long long) n_in - hist_len + k;
-    float2 x = v < 0 ? hist[(size_t) row * hist_len + hist_len + v] : in[(size_t) row * in_stride + v];
-    hist_next[(size_t) row * hist_len + k] = x;
+    const long long v = (long long) n_in - hist_len + k;
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {  // gridDim.y <= 65535
+        float2 x = v < 0 ? hist[(size_t) row * hist_len + hist_len + v] : in[(size_t) row * in_stride + v];
+        hist_next[(size_t) row * hist_len + k] = x;
+    }
 }
 
 __global__ void quad_demod_kernel(const float2 *in, size_t in_stride, float2 *prev, float gain, const float *atan_table,
-                                  float *out, size_t out_stride, int n_in) {
+                                  float *out, size_t out_stride, int n_in, int rows) {
     __shared__ float atan_s[257];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) {
         atan_s[i] = atan_table[i];
     }
     __syncthreads();
-    const int row = blockIdx.y;
-    const float2 *x = in + (size_t) row * in_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
-        float2 before = i > 0 ? x[i - 1] : prev[row];
-        out[(size_t) row * out_stride + i] = sdrm_quad_demod_sample(x[i], before, gain, atan_s);
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {  // gridDim.y <= 65535
+        const float2 *x = in + (size_t) row * in_stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+            float2 before = i > 0 ? x[i - 1] : prev[row];
+            out[(size_t) row * out_stride + i] = sdrm_quad_demod_sample(x[i], before, gain, atan_s);
+        }
     }
 }
 
@@ -500,13 +509,25 @@ __global__ void quad_demod_carry_kernel(const float2 *in, size_t in_stride, floa
 template <int D, bool FAST, bool ALIGNED, bool TP>
 int launch_tile_tp(const FirParams &p, int rows, int tiles, size_t smem, cudaStream_t stream) {
     auto kernel = fir_tile_kernel<D, FAST, ALIGNED, TP>;
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (err != cudaSuccess) {
-        return -(int) err - 1000;
+    cudaError_t err = cudaSuccess;
+    // Function attributes are per device and sticky: set them once per (instantiation, device) for the largest size this
+    // instantiation can ask for (two stages), not on every launch (~10 us each, most of a single-handle call's launch time).
+    static std::atomic<bool> configured[kMaxDevices];
+    int device = 0;
+    cudaGetDevice(&device);
+    if (device < 0 || device >= kMaxDevices || !configured[device].load(std::memory_order_acquire)) {
+        const size_t stage = (size_t) ((((kTile - 1) * D + 1 + kTapBlock + 2 + kSlack) + 1) & ~1) + kTapBlock;
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (2 * stage * sizeof(float2)));
+        if (err != cudaSuccess) {
+            return -(int) err - 1000;
+        }
+        // Same (maximum) shared-memory carveout as the tail kernel: an SM whose carveout was sized for one of the two kernels
+        // alone cannot take CTAs of the other until it drains, which serialises the filters of call k+1 against the tail of call k.
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (device >= 0 && device < kMaxDevices) {
+            configured[device].store(true, std::memory_order_release);
+        }
     }
-    // Same (maximum) shared-memory carveout as the tail kernel: an SM whose carveout was sized for one of the two kernels
-    // alone cannot take CTAs of the other until it drains, which serialises the filters of call k+1 against the tail of call k.
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid((unsigned) rows, (unsigned) tiles);
     kernel<<<grid, kThreads, smem, stream>>>(p);
     err = cudaGetLastError();
@@ -544,6 +565,7 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
     p.phase = a->phase;
     p.n_in = a->n_in;
     p.n_out = a->n_out;
+    p.rows = a->rows;
     p.out_mode = a->out_mode;
     p.out = a->out;
     p.out_stride = a->out_stride;
@@ -567,7 +589,7 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
         const int n_segs = kDecOutputs + (a->n_taps + a->decimation - 1) / a->decimation;
         const size_t dec_smem = ((size_t) n_segs * seg_len + a->n_taps) * sizeof(float2);
         if (dec_smem <= 200 * 1024) {
-            dim3 dgrid((unsigned) ((a->n_out + kDecOutputs - 1) / kDecOutputs), (unsigned) a->rows);
+            dim3 dgrid((unsigned) ((a->n_out + kDecOutputs - 1) / kDecOutputs), (unsigned) (a->rows < kMaxGridY ? a->rows : kMaxGridY));
             cudaError_t derr;
             if (a->fast) {
                 derr = cudaFuncSetAttribute(fir_dec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_smem);
@@ -582,7 +604,7 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
             derr = cudaGetLastError();
             return derr == cudaSuccess ? 0 : -(int) derr - 1000;
         }
-        dim3 grid((unsigned) ((a->n_out + 127) / 128), (unsigned) a->rows);
+        dim3 grid((unsigned) ((a->n_out + 127) / 128), (unsigned) (a->rows < kMaxGridY ? a->rows : kMaxGridY));
         if (a->fast) {
             fir_generic_kernel<true><<<grid, 128, 0, stream>>>(p);
         } else {
@@ -642,9 +664,9 @@ extern "C" int sdrm_cu_hist_update(const void *in, size_t in_stride, const void 
     if (rows <= 0 || hist_len <= 0) {
         return 0;
     }
-    dim3 grid((unsigned) ((hist_len + 255) / 256), (unsigned) rows);
+    dim3 grid((unsigned) ((hist_len + 255) / 256), (unsigned) (rows < kMaxGridY ? rows : kMaxGridY));
     hist_update_kernel<<<grid, 256, 0, (cudaStream_t) stream_ptr>>>((const float2 *) in, in_stride, (const float2 *) hist,
-                                                                    (float2 *) hist_next, hist_len, n_in);
+                                                                    (float2 *) hist_next, hist_len, n_in, rows);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }
@@ -659,9 +681,9 @@ extern "C" int sdrm_cu_quad_demod(const void *in, size_t in_stride, void *prev, 
     if (blocks > 1024) {
         blocks = 1024;
     }
-    dim3 grid((unsigned) blocks, (unsigned) rows);
+    dim3 grid((unsigned) blocks, (unsigned) (rows < kMaxGridY ? rows : kMaxGridY));
     quad_demod_kernel<<<grid, 256, 0, stream>>>((const float2 *) in, in_stride, (float2 *) prev, gain, atan_table, out,
-                                                out_stride, n_in);
+                                                out_stride, n_in, rows);
     quad_demod_carry_kernel<<<(rows + 127) / 128, 128, 0, stream>>>((const float2 *) in, in_stride, (float2 *) prev, n_in, rows);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;

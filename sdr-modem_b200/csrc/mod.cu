@@ -401,6 +401,9 @@ extern "C" int sdrm_cu_interp_fir(const sdrm_interp_args *a, void *stream_ptr) {
             if (bx > 2048) {
                 bx = 2048;
             }
+            if (a->n_ch > 65535) {
+                return -22;  // channel-major output puts the channel in gridDim.y; batches use the grouped layout
+            }
             dim3 grid((unsigned) bx, (unsigned) a->n_ch);
             if (a->in_is_bytes) {
                 if (a->branch_taps <= 8) {

@@ -101,23 +101,24 @@ __global__ void __launch_bounds__(64) nco_walk_kernel(const float *__restrict__ 
 template <bool MULTIPLY>
 __global__ void nco_rotate_kernel(const float2 *__restrict__ in, size_t in_stride, const float *__restrict__ phases,
                                   size_t phase_stride, const float *__restrict__ amplitude, float2 *__restrict__ out,
-                                  size_t out_stride, int n) {
-    const int ch = blockIdx.y;
-    const double amp = (double) amplitude[ch];
-    const float *ph = phases + (size_t) ch * phase_stride;
-    const float2 *x = MULTIPLY ? in + (size_t) ch * in_stride : nullptr;
-    float2 *y = out + (size_t) ch * out_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double s;
-        double c;
-        sincos((double) ph[i], &s, &c);
-        const float cr = (float) (c * amp);
-        const float ci = (float) (s * amp);
-        if (MULTIPLY) {
-            const float2 a = x[i];
-            y[i] = make_float2(__fsub_rn(__fmul_rn(a.x, cr), __fmul_rn(a.y, ci)), __fadd_rn(__fmul_rn(a.x, ci), __fmul_rn(a.y, cr)));
-        } else {
-            y[i] = make_float2(cr, ci);
+                                  size_t out_stride, int n, int n_ch) {
+    for (int ch = blockIdx.y; ch < n_ch; ch += gridDim.y) {  // gridDim.y <= 65535
+        const double amp = (double) amplitude[ch];
+        const float *ph = phases + (size_t) ch * phase_stride;
+        const float2 *x = MULTIPLY ? in + (size_t) ch * in_stride : nullptr;
+        float2 *y = out + (size_t) ch * out_stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            double s;
+            double c;
+            sincos((double) ph[i], &s, &c);
+            const float cr = (float) (c * amp);
+            const float ci = (float) (s * amp);
+            if (MULTIPLY) {
+                const float2 a = x[i];
+                y[i] = make_float2(__fsub_rn(__fmul_rn(a.x, cr), __fmul_rn(a.y, ci)), __fadd_rn(__fmul_rn(a.x, ci), __fmul_rn(a.y, cr)));
+            } else {
+                y[i] = make_float2(cr, ci);
+            }
         }
     }
 }
@@ -134,13 +135,13 @@ extern "C" int sdrm_cu_nco(const sdrm_nco_args *a, void *stream_ptr) {
     if (blocks_x > 64) {
         blocks_x = 64;
     }
-    dim3 grid((unsigned) blocks_x, (unsigned) a->n_ch);
+    dim3 grid((unsigned) blocks_x, (unsigned) (a->n_ch < 65535 ? a->n_ch : 65535));
     if (a->in != nullptr) {
         nco_rotate_kernel<true><<<grid, 256, 0, stream>>>((const float2 *) a->in, a->in_stride, a->phases, a->phase_stride,
-                                                          a->amplitude, (float2 *) a->out, a->out_stride, a->n);
+                                                          a->amplitude, (float2 *) a->out, a->out_stride, a->n, a->n_ch);
     } else {
         nco_rotate_kernel<false><<<grid, 256, 0, stream>>>(nullptr, 0, a->phases, a->phase_stride, a->amplitude,
-                                                           (float2 *) a->out, a->out_stride, a->n);
+                                                           (float2 *) a->out, a->out_stride, a->n, a->n_ch);
     }
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;

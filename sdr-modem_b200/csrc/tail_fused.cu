@@ -30,6 +30,8 @@
 // src/dsp/mmse_fir_interpolator.c:188-191; src/dsp/fir_filter.c:116-121; src/dsp/fsk_demod.c:106.
 
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 
 #include "sdrm_cuda.h"
@@ -688,11 +690,26 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
     void (*kernel)(const sdrm_tail_args) =
         !has_dc ? demod_tail_kernel<1, 2>
                 : (args->div_steps == 1 ? demod_tail_kernel<4, 1> : (args->div_steps == 2 ? demod_tail_kernel<4, 2> : demod_tail_kernel<4, 0>));
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (err != cudaSuccess) {
-        return -(int) err - 1000;
+    // function attributes once per (variant, device), sized for the largest ring (fir.cu does the same): not per launch
+    static std::atomic<bool> configured[4][64];
+    const int variant = !has_dc ? 3 : (args->div_steps == 1 ? 1 : (args->div_steps == 2 ? 2 : 0));
+    int device = 0;
+    cudaGetDevice(&device);
+    cudaError_t err = cudaSuccess;
+    if (device < 0 || device >= 64 || !configured[variant][device].load(std::memory_order_acquire)) {
+        int optin = 0;
+        err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (err == cudaSuccess) {
+            err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        }
+        if (err != cudaSuccess) {
+            return -(int) err - 1000;
+        }
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // see fir.cu
+        if (device >= 0 && device < 64) {
+            configured[variant][device].store(true, std::memory_order_release);
+        }
     }
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // see fir.cu
     kernel<<<blocks, (prod + 1) * 32, smem, stream>>>(*args);
     err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;

@@ -37,6 +37,7 @@ struct channel_state {
 };
 
 struct sdrm_doppler_batch_t {
+    int device; /* the NCO batch's device: staging buffers and copies must be issued with it current */
     uint32_t n_ch;
     uint32_t max_len;
     double sampling_freq;
@@ -102,7 +103,15 @@ int sdrm_doppler_batch_create(uint32_t n_channels, const sdrm_doppler_channel *c
             return -1;
         }
     }
-    int code = sdrm_nco_batch_create(n_channels, 1.0F, sampling_freq, max_output_buffer_length, device, &b->nco);
+    int code = 0;
+    if (device >= 0) {
+        b->device = device;
+    } else {
+        code = sdrm_cuda_code(cudaGetDevice(&b->device), "cudaGetDevice");
+    }
+    if (code == 0) {
+        code = sdrm_nco_batch_create(n_channels, 1.0F, sampling_freq, max_output_buffer_length, b->device, &b->nco);
+    }
     if (code != 0) {
         sdrm_doppler_batch_destroy(b);
         return code;
@@ -191,6 +200,8 @@ int sdrm_doppler_batch_process(sdrm_doppler_batch *b, int direction, const float
     if (len == 0) {
         return 0;
     }
+    /* a worker thread's current device is 0 until it says otherwise: the staging buffers must live where the NCO runs */
+    SDRM_CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t stream = (cudaStream_t) sdrm_nco_batch_stream(b->nco);
     if (b->d_in == NULL) {
         b->stride = sdrm_round_up((size_t) b->max_len, 2) + 2;
@@ -215,6 +226,9 @@ void sdrm_doppler_batch_destroy(sdrm_doppler_batch *b) {
         return;
     }
     sdrm_nco_batch_destroy(b->nco);
+    if (b->d_in != NULL || b->d_out != NULL) {
+        cudaSetDevice(b->device);
+    }
     cudaFree(b->d_in);
     cudaFree(b->d_out);
     free(b->ch);

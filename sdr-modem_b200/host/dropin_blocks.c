@@ -202,11 +202,12 @@ static void fir_core_process(struct fir_core *f, const void *input, size_t input
 
 /* fir_filter: reference src/dsp/fir_filter.h:29-35. The struct is opaque here (the reference's fields describe its
  * host working buffers; nothing outside src/dsp reads them). */
-struct fir_filter_t {
+/* fir_filter: reference src/dsp/fir_filter.h:9-35. The public struct (the reference's field layout) is the head of the
+ * handle; the device-side state follows it. */
+struct fir_filter_impl {
+    struct fir_filter_t pub; /* first: a fir_filter* is the address of this member */
     struct fir_core core;
-    float *taps;     /* the caller's malloc: owned from a successful create on, as in fir_filter.c:58,171-173 */
-    float *reversed; /* taps_len floats, reversed (fir_filter.c:27), for fir_filter_process_float_single */
-    size_t taps_len;
+    float *reversed; /* taps_len floats, reversed (fir_filter.c:27): pub.taps[0], and fir_filter_process_float_single */
 };
 
 int fir_filter_create(uint8_t decimation, float *taps, size_t taps_len, size_t max_input_buffer_length, size_t num_bytes,
@@ -214,47 +215,68 @@ int fir_filter_create(uint8_t decimation, float *taps, size_t taps_len, size_t m
     if (taps == NULL) {
         return -1;
     }
-    struct fir_filter_t *f = calloc(1, sizeof(*f));
+    struct fir_filter_impl *f = calloc(1, sizeof(*f));
     if (f == NULL) {
         return -ENOMEM;
     }
     /* from here on the filter owns the taps, also when create fails (fir_filter.c:58 followed by fir_filter_destroy) */
-    f->taps = taps;
-    f->taps_len = taps_len;
+    f->pub.original_taps = taps;
+    f->pub.taps_len = taps_len;
+    f->pub.alignment = 16;
+    /* the reference rejects an unparsable VOLK_ALIGNMENT override here (fir_filter.c:44-51); the value has no other use */
+    const char *alignment = getenv("VOLK_ALIGNMENT");
+    if (alignment != NULL) {
+        f->pub.alignment = (size_t) strtol(alignment, NULL, 10);
+        if (f->pub.alignment == 0) {
+            SDRM_LOG_ERROR("invalid VOLK_ALIGNMENT specified: %s", alignment);
+            fir_filter_destroy(&f->pub);
+            return -1;
+        }
+    }
     int code = fir_core_init(&f->core, decimation, taps, taps_len, max_input_buffer_length, num_bytes);
     if (code == 0) {
-        f->reversed = malloc(sizeof(float) * taps_len);
+        f->reversed = malloc(sizeof(float) * (taps_len == 0 ? 1 : taps_len));
         if (f->reversed == NULL) {
             code = -ENOMEM;
         }
     }
     if (code != 0) {
-        fir_filter_destroy(f);
+        fir_filter_destroy(&f->pub);
         return code;
     }
     for (size_t i = 0; i < taps_len; i++) {
         f->reversed[i] = taps[taps_len - 1 - i];
     }
-    *filter = f;
+    f->pub.decimation = decimation;
+    f->pub.taps = &f->reversed;
+    f->pub.aligned_taps_len = 1;
+    f->pub.history_offset = taps_len - 1;
+    f->pub.working_len_total = max_input_buffer_length + f->pub.history_offset;
+    f->pub.max_input_buffer_length = max_input_buffer_length;
+    f->pub.output = f->core.output;
+    f->pub.output_len = max_input_buffer_length / decimation + 1;
+    f->pub.num_bytes = num_bytes;
+    *filter = &f->pub;
     return 0;
 }
 
 void fir_filter_process(const void *input, size_t input_len, void **output, size_t *output_len, fir_filter *filter) {
-    fir_core_process(&filter->core, input, input_len, output, output_len);
+    fir_core_process(&((struct fir_filter_impl *) filter)->core, input, input_len, output, output_len);
 }
 
 /* One output from taps_len host floats, no state (fir_filter.c:116-121). The reference rounds the pointer down to its
  * 16-byte alignment and runs the dot product over (input - k .. input + taps_len) with k leading zero taps; the zeros
  * only matter when a sample in front of `input` is not finite, and that case is kept. */
 float fir_filter_process_float_single(const float *input, fir_filter *filter) {
+    const struct fir_filter_impl *f = (const struct fir_filter_impl *) filter;
     const size_t lead = ((size_t) input & 15u) / sizeof(float);
     const float *p = input - lead;
     float acc = 0.0f;
     for (size_t i = 0; i < lead; i++) {
         acc += p[i] * 0.0f;
     }
-    for (size_t i = 0; i < filter->taps_len; i++) {
-        acc += input[i] * filter->reversed[i];
+    for (size_t i = 0; i < f->pub.taps_len; i++) {
+        acc += input[i] * f->reversed[i];
     }
     return acc;
 }
@@ -263,10 +285,11 @@ void fir_filter_destroy(fir_filter *filter) {
     if (filter == NULL) {
         return;
     }
-    fir_core_free(&filter->core);
-    free(filter->taps);
-    free(filter->reversed);
-    free(filter);
+    struct fir_filter_impl *f = (struct fir_filter_impl *) filter;
+    fir_core_free(&f->core);
+    free(f->pub.original_taps);
+    free(f->reversed);
+    free(f);
 }
 
 struct lpf_t {
@@ -519,6 +542,7 @@ struct clock_mm_t {
     int *d_error;
     float *h_pack;
     float *output;
+    int history; /* host mirror of the carried sample count (the reference's history_offset) */
     cudaStream_t stream;
 };
 
@@ -606,22 +630,27 @@ void clock_mm_process(const float *input, size_t input_len, float **output, size
     a.error_flag = c->d_error;
     ok = ok && sdrm_launch_code(sdrm_cu_clock_mm(&a, c->stream), "clock recovery") == 0;
     uint32_t produced = 0;
+    sdrm_clock_state after;
+    memset(&after, 0, sizeof(after));
     ok = ok && cudaMemcpyAsync(&produced, c->d_out_len, sizeof(produced), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(&after, c->d_state, sizeof(after), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
     ok = ok && sdrm_cuda_code(cudaStreamSynchronize(c->stream), "clock_mm_process") == 0;
     if (!ok) {
         return;
     }
     c->head += (long long) input_len;
-    if (produced > 0) {
-        if (cudaMemcpy(c->output, c->d_soft, (size_t) produced * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
-            return;
-        }
-        *output = c->output;
+    /* the reference returns NULL / 0 while history + input is still shorter than the interpolator's 8 taps
+     * (clock_recovery_mm.c:94-99) and its output buffer, with any length including 0, otherwise */
+    const size_t working_len = (size_t) c->history + input_len;
+    c->history = after.history;
+    if (working_len < 8) {
+        return;
     }
-    /* the reference returns NULL / 0 while it is still collecting its first 8 samples and a valid pointer otherwise */
-    if (produced == 0) {
-        *output = c->output;
+    if (produced > 0 &&
+        cudaMemcpy(c->output, c->d_soft, (size_t) produced * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        return;
     }
+    *output = c->output;
     *output_len = produced;
 }
 

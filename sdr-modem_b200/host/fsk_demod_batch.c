@@ -38,6 +38,7 @@ struct sdrm_fsk_demod_batch_t {
     uint32_t n_ch_pad;
     int fast;
     int want_soft;
+    uint32_t aid; /* measurement aids (sdrm_internal.h), never reachable through the public flags */
 
     /* lpf1 + quad */
     void *d_taps1;
@@ -117,7 +118,8 @@ static int set_device(const sdrm_fsk_demod_batch *b) { return sdrm_cuda_code(cud
 
 int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_fsk_demod_batch **batch) {
     if (config == NULL || batch == NULL || config->n_channels == 0 || config->decimation == 0 ||
-        config->max_input_buffer_length == 0 || config->baud_rate == 0 || config->deviation == 0) {
+        config->max_input_buffer_length == 0 || config->baud_rate == 0 || config->deviation == 0 ||
+        (config->flags & ~(SDRM_FLAG_FAST_FMA | SDRM_FLAG_SOFT_OUT)) != 0) {
         return -1;
     }
     sdrm_fsk_demod_batch *b = calloc(1, sizeof(*b));
@@ -427,7 +429,7 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     ca.out_stride = b->out_stride;
     ca.out_len = b->d_out_len[slot];
     ca.max_out = (int) (b->cfg.max_symbols_per_call != 0 ? b->cfg.max_symbols_per_call : b->cfg.max_input_buffer_length);
-    if (b->cfg.flags & 0x40000000u) {
+    if (b->aid & SDRM_AID_NO_CLOCK_LOOP) {
         ca.max_out = 0; /* measurement aid: the clock loop never runs (results are invalid) */
     }
     ca.error_flag = b->d_error;
@@ -436,7 +438,7 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
         b->pos_l = (int) (((long long) b->pos_l + n_rows) % b->dc_len);
         b->pos_x = (int) (((long long) b->pos_x + n_rows) % b->dx_len);
     }
-    if (b->cfg.flags & 0x80000000u) {
+    if (b->aid & SDRM_AID_NO_TAIL) {
         code = 0; /* measurement aid: filters only, no tail (results are meaningless) */
     } else {
         code = sdrm_launch_code(sdrm_cu_demod_tail(&ca, b->s_tail), "dc blocker + clock recovery");
@@ -563,8 +565,8 @@ int sdrm_fsk_demod_batch_submit_i16(sdrm_fsk_demod_batch *b, const int16_t *inpu
 }
 
 int sdrm_fsk_demod_batch_fetch(sdrm_fsk_demod_batch *b, int8_t *output, float *soft, size_t out_stride, uint32_t *output_len) {
-    if (b == NULL || b->fetched >= b->submitted) {
-        return -1;
+    if (b == NULL || b->fetched >= b->submitted || (soft != NULL && !b->want_soft)) {
+        return -1; /* nothing is enqueued and the call stays un-fetched */
     }
     int code = set_device(b);
     if (code != 0) return code;
@@ -577,9 +579,6 @@ int sdrm_fsk_demod_batch_fetch(sdrm_fsk_demod_batch *b, int8_t *output, float *s
                                         b->s_out));
     }
     if (soft != NULL) {
-        if (!b->want_soft) {
-            return -1;
-        }
         SDRM_CUDA_TRY(cudaMemcpy2DAsync(soft, out_stride * sizeof(float), b->d_soft[slot], b->out_stride * sizeof(float),
                                         width * sizeof(float), b->n_ch, cudaMemcpyDeviceToHost, b->s_out));
     }
@@ -671,6 +670,28 @@ void *sdrm_fsk_demod_batch_stream(sdrm_fsk_demod_batch *b) { return b == NULL ? 
 
 void *sdrm_fsk_demod_batch_tail_stream(sdrm_fsk_demod_batch *b) { return b == NULL ? NULL : (void *) b->s_tail; }
 
+void *sdrm_fsk_demod_batch_out_stream(sdrm_fsk_demod_batch *b) { return b == NULL ? NULL : (void *) b->s_out; }
+
+/* Device-resident consumers: orders `stream` behind the tail of the most recently enqueued call, whose results
+ * sdrm_fsk_demod_batch_device_outputs points at. */
+int sdrm_fsk_demod_batch_wait_outputs(sdrm_fsk_demod_batch *b, void *stream) {
+    if (b == NULL || b->submitted == 0) {
+        return -1;
+    }
+    int code = set_device(b);
+    if (code != 0) return code;
+    SDRM_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t) stream, b->ev_tail[(b->submitted - 1) % SLOTS], 0));
+    return 0;
+}
+
+int sdrm_debug_set_measurement_aid(sdrm_fsk_demod_batch *b, uint32_t mask) {
+    if (b == NULL) {
+        return -1;
+    }
+    b->aid = mask;
+    return 0;
+}
+
 uint64_t sdrm_fsk_demod_batch_launch_count(const sdrm_fsk_demod_batch *b) { return b == NULL ? 0 : b->launches; }
 
 int sdrm_fsk_demod_batch_error_flags(sdrm_fsk_demod_batch *b) {
@@ -729,16 +750,12 @@ void sdrm_fsk_demod_batch_destroy(sdrm_fsk_demod_batch *b) {
     free(b);
 }
 
-void *sdrm_pinned_alloc(size_t bytes) {
-    void *p = NULL;
-    if (cudaHostAlloc(&p, bytes == 0 ? 1 : bytes, cudaHostAllocDefault) != cudaSuccess) {
-        return NULL;
-    }
-    return p;
-}
+void *sdrm_pinned_alloc(size_t bytes) { return sdrm_pinned_alloc_near_device(bytes, -1); }
+
+int sdrm_pinned_region_release(void *p); /* affinity.c */
 
 void sdrm_pinned_free(void *p) {
-    if (p != NULL) {
+    if (p != NULL && !sdrm_pinned_region_release(p)) {
         cudaFreeHost(p);
     }
 }
@@ -747,7 +764,7 @@ const char *sdrm_version(void) {
     static char text[96];
     int runtime = 0;
     cudaRuntimeGetVersion(&runtime);
-    snprintf(text, sizeof(text), "sdr-modem_b200 0.1.0; sm_100a; CUDA runtime %d", runtime);
+    snprintf(text, sizeof(text), "sdr-modem_b200 0.2.0; sm_100a; CUDA runtime %d", runtime);
     return text;
 }
 

@@ -39,6 +39,9 @@ struct sdrm_rx_group_t {
     int thread_started;
     volatile uint64_t blocks_done;
     int failed;
+    uint8_t *session_failed; /* [n]: a session whose client could not be written to is no longer served (the reference's
+                                dsp_worker thread ends on the first failed write, src/dsp_worker.c:93-103) */
+    volatile uint32_t sessions_failed;
 };
 
 static int write_all(const uint8_t *buffer, size_t len, int fd) {
@@ -63,14 +66,16 @@ static int deliver(sdrm_rx_group *g) {
         const sdrm_rx_session *s = &g->rows[r];
         const int8_t *symbols = g->h_symbols + (size_t) r * g->cap;
         const size_t len = g->h_lens[r];
-        if (len == 0) {
+        if (len == 0 || g->session_failed[r]) {
             continue;
         }
         if (s->sink != NULL) {
             s->sink(s->sink_ctx, s->id, symbols, len);
         } else if (s->client_socket >= 0) {
             if (write_all((const uint8_t *) symbols, len, s->client_socket) != 0) {
-                SDRM_LOG_ERROR("[%d] unable to write demod data to the client", s->id);
+                SDRM_LOG_ERROR("[%d] unable to write demod data to the client: session stopped", s->id);
+                g->session_failed[r] = 1;
+                g->sessions_failed++;
             }
         }
     }
@@ -134,12 +139,14 @@ static void *rx_group_thread(void *arg) {
             code = enqueue_block(g, input, len, (int) (k % IN_FLIGHT));
         }
         complete_buffer_processing(g->queue);
+        if (code != 0 && !(len > g->buffer_size)) {
+            /* a block that could not be enqueued leaves every session's stream with a hole: stop, do not skip */
+            SDRM_LOG_ERROR("rx group: block %llu failed with %d, group stopped", (unsigned long long) k, code);
+            g->failed = 1;
+            break;
+        }
         if (code != 0 || len == 0) {
-            if (code != 0 && code != -1) {
-                g->failed = 1;
-                break;
-            }
-            continue;
+            continue; /* oversize block: rejected like the reference's blocks reject it (NULL / 0 output) */
         }
         k++;
         in_flight++;
@@ -246,7 +253,8 @@ int sdrm_rx_group_create(const sdrm_rx_group_config *config, const sdrm_rx_sessi
     if (code == 0) {
         g->h_symbols = malloc((size_t) n_sessions * g->cap);
         g->h_lens = calloc(n_sessions, sizeof(uint32_t));
-        if (g->h_symbols == NULL || g->h_lens == NULL) {
+        g->session_failed = calloc(n_sessions, 1);
+        if (g->h_symbols == NULL || g->h_lens == NULL || g->session_failed == NULL) {
             code = -ENOMEM;
         }
     }
@@ -272,6 +280,10 @@ void sdrm_rx_group_shutdown(sdrm_rx_group *g) {
 }
 
 uint64_t sdrm_rx_group_blocks_done(const sdrm_rx_group *g) { return g->blocks_done; }
+
+int sdrm_rx_group_failed(const sdrm_rx_group *g) { return g == NULL ? -1 : g->failed; }
+
+uint32_t sdrm_rx_group_sessions_failed(const sdrm_rx_group *g) { return g == NULL ? 0 : g->sessions_failed; }
 
 void sdrm_rx_group_destroy(sdrm_rx_group *g) {
     if (g == NULL) {
@@ -300,6 +312,7 @@ void sdrm_rx_group_destroy(sdrm_rx_group *g) {
     }
     free(g->h_symbols);
     free(g->h_lens);
+    free(g->session_failed);
     free(g->rows);
     free(g);
 }

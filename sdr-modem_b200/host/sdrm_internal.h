@@ -45,6 +45,14 @@ static inline int sdrm_launch_code(int code, const char *what) {
     return -1;
 }
 
+/* Measurement aids of the batched demodulator (tools/probe_*.py, bench.py --debug-no-tail). They make the results invalid,
+ * so they are not public flags: sdrm_fsk_demod_batch_create rejects unknown flag bits, and these are set through
+ * sdrm_debug_set_measurement_aid, which no installed header declares. */
+#define SDRM_AID_NO_CLOCK_LOOP 1u /* the tail runs, the clock loop emits nothing */
+#define SDRM_AID_NO_TAIL 2u       /* filters only */
+struct sdrm_fsk_demod_batch_t;
+int sdrm_debug_set_measurement_aid(struct sdrm_fsk_demod_batch_t *batch, uint32_t mask);
+
 /* cudaMalloc + zero fill */
 int sdrm_dev_zalloc(void **p, size_t bytes);
 

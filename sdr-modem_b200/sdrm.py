@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libsdrmodem_b200.so")
 FLAG_FAST_FMA = 1
 FLAG_SOFT_OUT = 2
 MAX_IN_FLIGHT = 2
+# measurement aids (host/sdrm_internal.h): results become invalid; tools/probe_*.py and bench.py --debug-no-tail only
+AID_NO_CLOCK_LOOP = 1
+AID_NO_TAIL = 2
 
 
 class FskDemodBatchConfig(C.Structure):
@@ -41,6 +44,11 @@ def _load():
     lib.sdrm_pinned_alloc.restype = vp
     lib.sdrm_pinned_alloc.argtypes = [sz]
     lib.sdrm_pinned_free.argtypes = [vp]
+    lib.sdrm_pinned_alloc_near_device.restype = vp
+    lib.sdrm_pinned_alloc_near_device.argtypes = [sz, i32]
+    lib.sdrm_device_numa_node.argtypes = [i32]
+    lib.sdrm_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.sdrm_probe_h2d.argtypes = [i32, vp, vp, sz, i32, C.POINTER(C.c_double)]
     lib.sdrm_bind_thread_near_device.argtypes = [i32]
     lib.sdrm_cpulist_parse_count.argtypes = [C.c_char_p]
     lib.sdrm_fsk_demod_batch_create.argtypes = [C.POINTER(FskDemodBatchConfig), C.POINTER(vp)]
@@ -58,6 +66,10 @@ def _load():
     lib.sdrm_fsk_demod_batch_stream.argtypes = [vp]
     lib.sdrm_fsk_demod_batch_tail_stream.restype = vp
     lib.sdrm_fsk_demod_batch_tail_stream.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_out_stream.restype = vp
+    lib.sdrm_fsk_demod_batch_out_stream.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_wait_outputs.argtypes = [vp, vp]
+    lib.sdrm_debug_set_measurement_aid.argtypes = [vp, C.c_uint32]
     lib.sdrm_fsk_demod_batch_launch_count.restype = C.c_uint64
     lib.sdrm_fsk_demod_batch_launch_count.argtypes = [vp]
     lib.sdrm_fsk_demod_batch_error_flags.argtypes = [vp]
@@ -105,6 +117,23 @@ def _load():
     lib.sdrm_doppler_batch_stream.argtypes = [vp]
     lib.sdrm_doppler_batch_destroy.argtypes = [vp]
     lib.sdrm_doppler_batch_destroy.restype = None
+    # multi-device entry points (include/sdrm/sdrm_multi.h)
+    lib.sdrm_fsk_demod_multi_create.argtypes = [C.POINTER(FskDemodBatchConfig), C.POINTER(i32), C.c_uint32, C.POINTER(vp)]
+    lib.sdrm_fsk_demod_multi_submit.argtypes = [vp, vp, sz, sz]
+    lib.sdrm_fsk_demod_multi_submit_i16.argtypes = [vp, vp, sz, sz, C.c_float]
+    lib.sdrm_fsk_demod_multi_fetch.argtypes = [vp, vp, vp, sz, vp]
+    lib.sdrm_fsk_demod_multi_process.argtypes = [vp, vp, sz, sz, vp, vp, sz, vp]
+    lib.sdrm_fsk_demod_multi_sync.argtypes = [vp]
+    lib.sdrm_fsk_demod_multi_device_count.restype = C.c_uint32
+    lib.sdrm_fsk_demod_multi_device_count.argtypes = [vp]
+    lib.sdrm_fsk_demod_multi_shard.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(i32)]
+    lib.sdrm_fsk_demod_multi_batch.restype = vp
+    lib.sdrm_fsk_demod_multi_batch.argtypes = [vp, C.c_uint32]
+    lib.sdrm_fsk_demod_multi_launch_count.restype = C.c_uint64
+    lib.sdrm_fsk_demod_multi_launch_count.argtypes = [vp]
+    lib.sdrm_fsk_demod_multi_error_flags.argtypes = [vp]
+    lib.sdrm_fsk_demod_multi_destroy.argtypes = [vp]
+    lib.sdrm_fsk_demod_multi_destroy.restype = None
     # reference-named single-channel API
     lib.fsk_demod_create.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_uint8, C.c_uint32, C.c_bool, C.c_uint32,
                                      C.POINTER(vp)]
@@ -140,12 +169,27 @@ def bind_thread_near_device(device):
     return n
 
 
-class PinnedArray:
-    """numpy view over pinned host memory from sdrm_pinned_alloc."""
+def measure_fp32_peak(device=-1):
+    """(FMA peak, exact-mode FFMA2-pair rate) of the device's FP32 pipe in algorithmic TFLOP/s, measured now."""
+    fma, pair = C.c_double(), C.c_double()
+    _check(lib.sdrm_measure_fp32_peak(int(device), C.byref(fma), C.byref(pair)), "sdrm_measure_fp32_peak")
+    return fma.value, pair.value
 
-    def __init__(self, shape, dtype):
+
+def probe_h2d(device, host_ptr, d_ptr, nbytes, repeats):
+    """seconds of device time for `repeats` plain pinned host -> device copies of nbytes"""
+    sec = C.c_double()
+    _check(lib.sdrm_probe_h2d(int(device), C.c_void_p(host_ptr), C.c_void_p(d_ptr), nbytes, repeats, C.byref(sec)),
+           "sdrm_probe_h2d")
+    return sec.value
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from sdrm_pinned_alloc (device given: on that device's NUMA node)."""
+
+    def __init__(self, shape, dtype, device=-1):
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        self.ptr = lib.sdrm_pinned_alloc(self.nbytes)
+        self.ptr = lib.sdrm_pinned_alloc_near_device(self.nbytes, int(device))
         if not self.ptr:
             raise SdrmError("sdrm_pinned_alloc(%d) failed" % self.nbytes)
         buf = (C.c_char * self.nbytes).from_address(self.ptr)
@@ -168,16 +212,18 @@ class FskDemodBatch:
     """N x fsk_demod (reference src/dsp/fsk_demod.c) as one batched GPU session."""
 
     def __init__(self, n_channels, sampling_freq, baud_rate, deviation, decimation, transition_width, use_dc_block,
-                 max_input_buffer_length, max_symbols_per_call=0, fast=False, soft=False, device=-1, debug_flags=0):
+                 max_input_buffer_length, max_symbols_per_call=0, fast=False, soft=False, device=-1, measurement_aid=0):
         cfg = FskDemodBatchConfig(n_channels, sampling_freq, baud_rate, deviation, decimation, transition_width,
                                   bool(use_dc_block), max_input_buffer_length, max_symbols_per_call,
-                                  (FLAG_FAST_FMA if fast else 0) | (FLAG_SOFT_OUT if soft else 0) | debug_flags, device)
+                                  (FLAG_FAST_FMA if fast else 0) | (FLAG_SOFT_OUT if soft else 0), device)
         self.handle = C.c_void_p()
         self.n_channels = n_channels
         self.max_len = max_input_buffer_length
         self.capacity = max_symbols_per_call or max_input_buffer_length
         self.soft = soft
         _check(lib.sdrm_fsk_demod_batch_create(C.byref(cfg), C.byref(self.handle)), "sdrm_fsk_demod_batch_create")
+        if measurement_aid:
+            _check(lib.sdrm_debug_set_measurement_aid(self.handle, measurement_aid), "sdrm_debug_set_measurement_aid")
 
     # -- host buffers -------------------------------------------------------------------------------------------
     def process(self, iq):
@@ -251,6 +297,13 @@ class FskDemodBatch:
         return lib.sdrm_fsk_demod_batch_tail_stream(self.handle)
 
     @property
+    def out_stream(self):
+        return lib.sdrm_fsk_demod_batch_out_stream(self.handle)
+
+    def wait_outputs(self, stream):
+        _check(lib.sdrm_fsk_demod_batch_wait_outputs(self.handle, C.c_void_p(stream)), "sdrm_fsk_demod_batch_wait_outputs")
+
+    @property
     def launch_count(self):
         return lib.sdrm_fsk_demod_batch_launch_count(self.handle)
 
@@ -284,6 +337,81 @@ class FskDemodBatch:
     def close(self):
         if self.handle:
             lib.sdrm_fsk_demod_batch_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FskDemodMulti:
+    """N x fsk_demod partitioned over a list of CUDA devices by channel range (include/sdrm/sdrm_multi.h)."""
+
+    def __init__(self, devices, n_channels, sampling_freq, baud_rate, deviation, decimation, transition_width, use_dc_block,
+                 max_input_buffer_length, max_symbols_per_call=0, fast=False, soft=False):
+        cfg = FskDemodBatchConfig(n_channels, sampling_freq, baud_rate, deviation, decimation, transition_width,
+                                  bool(use_dc_block), max_input_buffer_length, max_symbols_per_call,
+                                  (FLAG_FAST_FMA if fast else 0) | (FLAG_SOFT_OUT if soft else 0), -1)
+        self.handle = C.c_void_p()
+        self.n_channels = n_channels
+        self.capacity = max_symbols_per_call or max_input_buffer_length
+        self.soft = soft
+        dev = (C.c_int * len(devices))(*devices)
+        _check(lib.sdrm_fsk_demod_multi_create(C.byref(cfg), dev, len(devices), C.byref(self.handle)),
+               "sdrm_fsk_demod_multi_create")
+
+    def submit(self, iq):
+        assert iq.ndim == 2 and iq.shape[0] == self.n_channels and iq.dtype == np.complex64 and iq.flags.c_contiguous
+        self._keep = iq
+        _check(lib.sdrm_fsk_demod_multi_submit(self.handle, iq.ctypes.data_as(C.c_void_p), iq.shape[1], iq.shape[1]),
+               "sdrm_fsk_demod_multi_submit")
+
+    def submit_ptr(self, host_ptr, in_stride, n):
+        _check(lib.sdrm_fsk_demod_multi_submit(self.handle, host_ptr, in_stride, n), "sdrm_fsk_demod_multi_submit")
+
+    def submit_i16_ptr(self, host_ptr, in_stride, n, scalar=2048.0):
+        _check(lib.sdrm_fsk_demod_multi_submit_i16(self.handle, host_ptr, in_stride, n, scalar),
+               "sdrm_fsk_demod_multi_submit_i16")
+
+    def fetch(self):
+        hard = np.zeros((self.n_channels, self.capacity), dtype=np.int8)
+        lens = np.zeros(self.n_channels, dtype=np.uint32)
+        soft = np.zeros((self.n_channels, self.capacity), dtype=np.float32) if self.soft else None
+        _check(lib.sdrm_fsk_demod_multi_fetch(self.handle, hard.ctypes.data_as(C.c_void_p),
+                                              soft.ctypes.data_as(C.c_void_p) if soft is not None else None,
+                                              hard.shape[1], lens.ctypes.data_as(C.c_void_p)), "sdrm_fsk_demod_multi_fetch")
+        return hard, lens, soft
+
+    def fetch_ptr(self, hard_ptr, out_stride, lens_ptr):
+        _check(lib.sdrm_fsk_demod_multi_fetch(self.handle, hard_ptr, None, out_stride, lens_ptr), "sdrm_fsk_demod_multi_fetch")
+
+    def process(self, iq):
+        self.submit(np.ascontiguousarray(iq, dtype=np.complex64))
+        return self.fetch()
+
+    def shards(self):
+        out = []
+        for g in range(lib.sdrm_fsk_demod_multi_device_count(self.handle)):
+            first, count, dev = C.c_uint32(), C.c_uint32(), C.c_int()
+            _check(lib.sdrm_fsk_demod_multi_shard(self.handle, g, C.byref(first), C.byref(count), C.byref(dev)), "shard")
+            out.append((first.value, count.value, dev.value))
+        return out
+
+    def sync(self):
+        _check(lib.sdrm_fsk_demod_multi_sync(self.handle), "sdrm_fsk_demod_multi_sync")
+
+    @property
+    def launch_count(self):
+        return lib.sdrm_fsk_demod_multi_launch_count(self.handle)
+
+    def error_flags(self):
+        return lib.sdrm_fsk_demod_multi_error_flags(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib.sdrm_fsk_demod_multi_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):

@@ -14,6 +14,7 @@ it. Two properties that do not depend on the size are checked instead:
   bound below is that figure with head room, not zero.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -125,14 +126,19 @@ def test_modulator_to_demodulator_round_trip_full_size(sdrm):
     assert max(lags) - min(lags) <= 1, sorted(lags)
 
 
-def test_c3_literal_chain_subset(sdrm, port, ref):
+@pytest.mark.parametrize("n_ch,calls", [(16, 2), (2, 19)], ids=["16ch_x_2calls", "2ch_x_19calls_second_rollover"])
+def test_c3_literal_chain_subset(sdrm, port, ref, n_ch, calls):
     """BASELINE configs[2], the literal dsp_worker chain: doppler_process_rx -> fsk_demod_create(2400000, 2400, 5000, 100,
     2000, true, 131072), i.e. a 9325-tap lpf1 (18 tap blocks) and a 2891-tap lpf2 decimating by 100, in 131072-sample calls.
-    The oracle manages 0.15 Msamples/s at this shape, so three channels with their own Doppler clocks and two calls each are
-    checked (SURVEY.md section 8d). The Doppler stage is compared with the reference build inside its trigonometric tolerance;
-    the demodulator is then bit-compared on exactly the samples the GPU Doppler stage produced."""
+    The oracle manages 0.15 Msamples/s at this shape, so a subset is checked: 16 channels with their own
+    Doppler clocks over two calls, and two channels over 19 calls = 2.49 M samples, so that the orbit model's second boundary
+    (one SGP4 evaluation per 2.4 M samples, reference src/dsp/doppler.c:150-175) is crossed in the middle of the last call.
+    The Doppler stage is compared with the reference build inside its trigonometric tolerance; the demodulator is then
+    bit-compared on exactly the samples the GPU Doppler stage produced."""
+    import concurrent.futures as cf
     from conftest import LUCKY7_TLE
-    fs, baud, chunk, calls, n_ch = 2400000, 2400, 131072, 2, 3
+    fs, baud, chunk = 2400000, 2400, 131072
+    assert n_ch >= 16 or calls * chunk > fs  # either the wide subset or the run across the second boundary
     shape = workloads.DemodShape("gmsk2400@2.4M", fs, baud, 5000, 100, 2000, True, chunk)
     iq = workloads.gfsk_channels(n_ch, calls * chunk, shape, seed=31, max_offset_hz=4000.0).numpy()
     lat, lon = float(np.float32(53.72)), float(np.float32(47.57))
@@ -141,17 +147,74 @@ def test_c3_literal_chain_subset(sdrm, port, ref):
                             chunk)
     corrected = np.concatenate([dop.process(iq[:, k * chunk:(k + 1) * chunk]) for k in range(calls)], axis=1)
     dop.close()
-    for c in range(n_ch):
-        want = ref.doppler(lat, lon, 0.0, fs, 437525000, 0, starts[c], chunk, LUCKY7_TLE).run(iq[c], chunk)
-        same = corrected[c].view(np.uint32) == want.view(np.uint32)
-        assert same.mean() > 0.99999 and np.abs(corrected[c] - want).max() < 1e-6, "doppler channel %d" % c
     batch = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, soft=True)
     try:
         hard, soft = batch.run_stream(corrected, chunk)
         assert batch.error_flags() == 0
     finally:
         batch.close()
-    for c in range(n_ch):
+
+    def check(c):
+        want = ref.doppler(lat, lon, 0.0, fs, 437525000, 0, starts[c], chunk, LUCKY7_TLE).run(iq[c], chunk)
+        same = corrected[c].view(np.uint32) == want.view(np.uint32)
+        assert same.mean() > 0.99999 and np.abs(corrected[c] - want).max() < 1e-6, "doppler channel %d" % c
         want_hard, want_soft = port.FskDemod(*shape.create_args, chunk).run(corrected[c], chunk)
         assert len(want_hard) > calls * chunk // 1000 - 80
         assert same_bits(hard[c], want_hard) and same_bits(soft[c], want_soft), "demod channel %d" % c
+        return len(want_hard)
+
+    with cf.ThreadPoolExecutor(min(n_ch, os.cpu_count() or 1)) as pool:  # the oracle's C code runs outside the GIL
+        counts = list(pool.map(check, range(n_ch)))
+    assert sum(counts) > 0
+
+
+def xorshift32_channels(n_bytes, seeds):
+    """xorshift32 payload bytes for many channels at once (seed 2000 + c), uint8 [channels][n_bytes]"""
+    x = np.array(seeds, dtype=np.uint32)
+    out = np.empty((len(seeds), n_bytes), dtype=np.uint8)
+    for i in range(n_bytes):
+        x ^= x << np.uint32(13)
+        x ^= x >> np.uint32(17)
+        x ^= x << np.uint32(5)
+        out[:, i] = x & np.uint32(0xFF)
+    return out
+
+
+def test_c4_full_size_sixteen_xorshift_packets(sdrm, port):
+    """BASELINE configs[3] at its judged size: 1024 channels, gfsk_mod_create(2.0, 2 pi 5000 / 19200, 0.5, 2048), sixteen
+    2048-byte packets per channel with carried phase and filter state, payload xorshift32(seed = 2000 + c). Every 16th channel
+    (64 of them, all packets, all 32768 output samples per packet) is compared with the oracle's modulator."""
+    import concurrent.futures as cf
+    import torch
+    from test_gpu_mod_nco import close_trig
+    n_ch, packet, packets, every = 1024, 2048, 16, 16
+    sps, sens = 2.0, float(np.float32(2 * np.pi * 5000 / 19200))
+    per_packet = packet * 8 * int(sps)
+    data = xorshift32_channels(packet * packets, [2000 + c for c in range(n_ch)])
+    assert np.array_equal(data[7, :64], workloads.xorshift_bytes(64, 2007))
+    d_data = torch.from_numpy(data).cuda()
+    mod = sdrm.GfskModBatch(n_ch, sps, sens, 0.5, packet)
+    out_stream = torch.cuda.ExternalStream(mod.stream)
+    d_out = [torch.empty((n_ch, per_packet), dtype=torch.complex64, device="cuda") for _ in range(2)]
+    got = np.empty((n_ch // every, packets * per_packet), dtype=np.complex64)
+    try:
+        for k in range(packets):
+            d_in = d_data[:, k * packet:(k + 1) * packet].contiguous()
+            mod.process_device(d_in.data_ptr(), packet, packet, d_out[k % 2].data_ptr(), per_packet)
+            mod.sync()
+            with torch.cuda.stream(out_stream):
+                got[:, k * per_packet:(k + 1) * per_packet] = d_out[k % 2][::every].cpu().numpy()
+        launches = mod.launch_count
+    finally:
+        mod.close()
+    assert launches >= 3 * packets
+
+    def check(i):
+        c = i * every
+        o = port.GfskMod(sps, sens, 0.5, packet)
+        want = np.concatenate([o.process(data[c, k * packet:(k + 1) * packet]) for k in range(packets)])
+        assert close_trig(got[i], want), "channel %d" % c
+        return True
+
+    with cf.ThreadPoolExecutor(os.cpu_count() or 1) as pool:
+        assert all(pool.map(check, range(n_ch // every)))

@@ -27,6 +27,18 @@ LUCKY7_TLE = ["LUCKY-7",
               "2 44406  97.5270  32.5584 0026284 107.4758 252.9348 15.12089395 37524"]
 
 
+def xorshift32_channels(n_bytes, seeds):
+    """xorshift32 payload bytes for many channels at once: uint8 [channels][n_bytes]"""
+    x = np.array(seeds, dtype=np.uint32)
+    out = np.empty((len(seeds), n_bytes), dtype=np.uint8)
+    for i in range(n_bytes):
+        x ^= x << np.uint32(13)
+        x ^= x >> np.uint32(17)
+        x ^= x << np.uint32(5)
+        out[:, i] = x & np.uint32(0xFF)
+    return out
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -40,11 +52,14 @@ def bench_c4(args):
     from oracle import ref
     import workloads
     n_ch, packet = args.channels, 2048
+    device = getattr(args, "device", 0)
     sps, sens = 2.0, float(np.float32(2 * np.pi * 5000 / 19200))
     out_per_packet = packet * 8 * int(sps)
-    mod = sdrm.GfskModBatch(n_ch, sps, sens, 0.5, packet, device=0)
+    mod = sdrm.GfskModBatch(n_ch, sps, sens, 0.5, packet, device=device)
     rng = np.random.default_rng(2000)
-    data = torch.from_numpy(rng.integers(0, 256, (2, n_ch, packet), dtype=np.uint8)).cuda()
+    # payload: xorshift32(seed = 2000 + c) per channel, two packets per channel, rotating
+    data = torch.from_numpy(xorshift32_channels(2 * packet, [2000 + c for c in range(n_ch)]).reshape(n_ch, 2, packet)
+                            .transpose(1, 0, 2).copy()).cuda()
     out = torch.empty((2, n_ch, out_per_packet), dtype=torch.complex64, device="cuda")
     stream = torch.cuda.ExternalStream(mod.stream)
 
@@ -67,19 +82,25 @@ def bench_c4(args):
     bytes_per_sample = 8 + 1.0 / (8 * sps)
     achieved = value * 1e6 * bytes_per_sample / 1e9
     cores = os.cpu_count() or 1
-    cpu_data = rng.integers(0, 256, (cores, packet), dtype=np.uint8)
-    sec, cnt = ref.bench_gfsk_mod(sps, sens, 0.5, cpu_data, cores, packets=200)
-    print(json.dumps({
+    cpu = None
+    if not getattr(args, "no_cpu", False):
+        cpu_data = rng.integers(0, 256, (cores, packet), dtype=np.uint8)
+        sec, cnt = ref.bench_gfsk_mod(sps, sens, 0.5, cpu_data, cores, packets=200)
+        cpu = {"value": cnt / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+               "sample": "%d channels x 200 packets of %d bytes" % (cores, packet)}
+    launches = int(mod.launch_count)
+    mod.close()
+    del data, out
+    return ({
         "metric": "modulated Msamples/s (output)", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%d channels x %d-byte packets, gfsk_mod sps 2, BT 0.5 (BASELINE configs[3])" % (n_ch, packet),
                    "l2": "2 x %.0f MB output buffers rotating" % (samples * 8 / 1e6)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "note": "8.06 algorithmic B per output sample; the float phase recurrence (one lane per channel, ~14 cycles "
-                             "per sample) bounds batches below a few thousand channels"},
-        "cpu_baseline": {"value": cnt / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                         "sample": "%d channels x 200 packets of %d bytes" % (cores, packet)},
-        "gpu_launches": int(mod.launch_count)}))
+                     "note": "8.06 algorithmic B per output sample; bounded by the serial float phase recurrence (one lane per "
+                             "channel, 20.5 cycles per sample: 0.34 ms per 32768-sample packet whatever the channel count, up to "
+                             "148 SMs x 4 warps x 32 lanes = 18944 channels) and, past that, by the double-precision sincos"},
+        "cpu_baseline": cpu, "gpu_launches": launches})
 
 
 def bench_c3(args):
@@ -88,13 +109,15 @@ def bench_c3(args):
     from oracle import ref
     import workloads
     n_ch, chunk = args.channels, 131072
+    device = getattr(args, "device", 0)
+    fast = getattr(args, "mode", "exact") == "fast"
     shape = workloads.DemodShape("gmsk2400@2.4M/chunk131072", 2400000, 2400, 5000, 100, 2000, True, chunk)
     flops, t1, t2 = workloads.demod_flops_per_sample(shape)
     lat, lon = float(np.float32(53.72)), float(np.float32(47.57))
     channels = [sdrm.doppler_channel(lat, lon, 0.0, 0, 1583840449 + c, LUCKY7_TLE) for c in range(n_ch)]
-    dop = sdrm.DopplerBatch(channels, shape.sampling_freq, 437525000, chunk, device=0)
+    dop = sdrm.DopplerBatch(channels, shape.sampling_freq, 437525000, chunk, device=device)
     cap = int(chunk / 100 / 10 * 1.2) + 64
-    demod = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=cap, device=0)
+    demod = sdrm.FskDemodBatch(n_ch, *shape.create_args, chunk, max_symbols_per_call=cap, device=device, fast=fast)
     t0 = time.time()
     iq = workloads.gfsk_channels(n_ch, 2 * chunk, shape, seed=3000, device="cuda", max_offset_hz=4000.0)
     bufs = [iq[:, i * chunk:(i + 1) * chunk].contiguous() for i in range(2)]
@@ -131,10 +154,14 @@ def bench_c3(args):
     step(0)
     stage = demod.stage_times()
     pk, kind = peaks()
-    peak = 148 * 128 * 2 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+    peak = getattr(args, "fp32_peak", None) or 148 * 128 * 2 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     achieved = value * 1e6 * flops / 1e12
     cores = os.cpu_count() or 1
     cpu = None
+    flags = demod.error_flags()
+    demod.close()
+    dop.close()
+    del bufs, corrected
     if not args.no_cpu:
         x = workloads.gfsk_channels(cores, chunk, shape, seed=3000, device="cpu", max_offset_hz=4000.0).numpy()
         t0 = time.time()
@@ -150,15 +177,16 @@ def bench_c3(args):
         sec = time.time() - t0
         cpu = {"value": cores * chunk / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
                "sample": "%d channels x %d samples (one call each), doppler_process_rx + fsk_demod_process" % (cores, chunk)}
-    print(json.dumps({
+    return ({
         "metric": "demodulated Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%d channels x doppler + %s, decim 100, dc on (BASELINE configs[2]); T1 = %d, T2 = %d"
-                               % (n_ch, shape.name, t1, t2), "mode": "exact", "input_gen_s": gen_s,
+                               % (n_ch, shape.name, t1, t2), "mode": "fast" if fast else "exact", "input_gen_s": gen_s,
                    "flop_per_sample": flops},
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "kernel_ms": stage[0], "kernel_frac": 4.0 * t1 * n_ch * chunk / (stage[0] * 1e-3) / 1e12 / peak,
                      "stage_ms": {"lpf1_quad": stage[0], "lpf2": stage[1], "dc_clock_tail": stage[2]}},
-        "cpu_baseline": cpu, "error_flags": demod.error_flags()}))
+        "cpu_baseline": cpu, "error_flags": flags})
 
 
 def bench_perf_shape(args):
@@ -202,14 +230,14 @@ def bench_perf_shape(args):
         sec, _ = ref.bench_fsk_demod(*shape.create_args, chunk, x, cores, passes=4)
         cpu = {"value": cores * 2 * chunk * 4 / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
                "sample": "%d channels x %d samples x 4 passes, one thread per channel" % (cores, 2 * chunk)}
-    print(json.dumps({
+    return ({
         "metric": "demodulated Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%d channels x %s, dc on (the reference's perf_fsk_modem shape); T1 = %d, T2 = %d"
                                % (n_ch, shape.name, t1, t2), "mode": "exact", "flop_per_sample": flops},
         "roofline": {"bound": "serial tail (dependent-issue latency), not a throughput roofline",
                      "stage_ms": {"lpf1_quad": stage[0], "lpf2": stage[1], "dc_clock_tail": stage[2]}},
-        "cpu_baseline": cpu, "error_flags": demod.error_flags()}))
+        "cpu_baseline": cpu, "error_flags": demod.error_flags()})
 
 
 def bench_c1(args):
@@ -225,10 +253,10 @@ def bench_c1(args):
             iq = workloads.gfsk_channels(1, n, shape, seed=1000, device="cpu").numpy()
         sec, symbols = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, 1, passes=1)
         out[name] = {"msamples_per_s": n / sec / 1e6, "seconds": sec, "samples": n, "symbols": int(symbols), "chunk": shape.chunk}
-    print(json.dumps({"metric": "demodulated Msamples/s", "value": out["c1_192k_9600"]["msamples_per_s"], "unit": "Msamples/s",
+    return ({"metric": "demodulated Msamples/s", "value": out["c1_192k_9600"]["msamples_per_s"], "unit": "Msamples/s",
                       "n_gpus": 0, "impl": "reference", "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "1 channel, 1 core, oracle/_ref strict build (BASELINE configs[0])"},
-                      "cpu_baseline": {"cores": 1, "kind": "reference"}, "shapes": out}))
+                      "cpu_baseline": {"cores": 1, "kind": "reference"}, "shapes": out})
 
 
 def bench_c3alt(args):
@@ -284,7 +312,7 @@ def bench_c3alt(args):
     ms = start.elapsed_time(end) / args.steps
     value = n_ch * chunk / (ms * 1e-3) / 1e6
     pk, kind = peaks()
-    print(json.dumps({
+    return ({
         "metric": "demodulated Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%d channels x doppler -> lpf(dec %d, cutoff 20 kHz, tw 10 kHz) -> fsk_demod(96 ksps, 2400 baud, "
@@ -292,7 +320,7 @@ def bench_c3alt(args):
         "roofline": {"bound": "hbm", "achieved": value * 1e6 * 24 / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": value * 1e6 * 24 / 1e9 / pk["hbm_gbs"],
                      "note": "24 algorithmic B per input sample: doppler 8 in + 8 out, lpf 8 in (+ 8/25 out)"},
-        "error_flags": demod.error_flags()}))
+        "error_flags": demod.error_flags()})
 
 
 def main():
@@ -302,24 +330,27 @@ def main():
     p.add_argument("--steps", type=int, default=None)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--mode", default="exact", choices=["exact", "fast"], help="c3: arithmetic mode of the demodulator")
+    p.add_argument("--device", type=int, default=0)
     args = p.parse_args()
     if args.config == "c4":
         args.channels = args.channels or 1024
         args.steps = args.steps or 50
-        bench_c4(args)
+        line = bench_c4(args)
     elif args.config == "c1":
-        bench_c1(args)
+        line = bench_c1(args)
     elif args.config == "c3alt":
         args.channels = args.channels or 1024
         args.steps = args.steps or 10
-        bench_c3alt(args)
+        line = bench_c3alt(args)
     elif args.config == "perf":
         args.steps = args.steps or 20
-        bench_perf_shape(args)
+        line = bench_perf_shape(args)
     else:
         args.channels = args.channels or 4096
         args.steps = args.steps or 3
-        bench_c3(args)
+        line = bench_c3(args)
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -16,9 +16,9 @@ n_ch, chunk, steps = 1024, 131072, 30
 shape = workloads.C2_THROUGHPUT
 iq = workloads.gfsk_channels(n_ch, 2 * chunk, shape, seed=1000, device="cuda")
 bufs = [iq[:, :chunk].contiguous(), iq[:, chunk:].contiguous()]
-for label, use_dc, flags in (("dc on", True, 0), ("dc off", False, 0), ("no tail", True, 0x80000000)):
+for label, use_dc, flags in (("dc on", True, 0), ("dc off", False, 0), ("no tail", True, sdrm.AID_NO_TAIL)):
     b = sdrm.FskDemodBatch(n_ch, 192000, 9600, 5000, 2, 2000, use_dc, chunk, max_symbols_per_call=int(chunk / 20 * 1.2) + 64,
-                           debug_flags=flags)
+                           measurement_aid=flags)
     fir = torch.cuda.ExternalStream(b.stream)
     tail = torch.cuda.ExternalStream(b.tail_stream)
     for k in range(3):

@@ -15,9 +15,9 @@ import workloads  # noqa: E402
 n_ch, chunk = 1024, 131072
 shape = workloads.C2_THROUGHPUT
 iq = workloads.gfsk_channels(n_ch, chunk, shape, seed=1000, device="cuda")
-for use_dc, flags in ((True, 0), (False, 0), (True, 0x40000000)):
+for use_dc, flags in ((True, 0), (False, 0), (True, sdrm.AID_NO_CLOCK_LOOP)):
     b = sdrm.FskDemodBatch(n_ch, 192000, 9600, 5000, 2, 2000, use_dc, chunk, max_symbols_per_call=int(chunk / 20 * 1.2) + 64,
-                           debug_flags=flags)
+                           measurement_aid=flags)
     b.set_profiling(True)
     times = []
     for k in range(4):
