@@ -307,51 +307,58 @@ def run_other_configs(args, world, rank, local_rank, fp32_peak):
     """BASELINE.json configs other than the headline one, each as {name, value, unit, ms_per_step, roofline_frac, ...}.
     N = 1: configs[3] (modulator, 1024 channels and at the channel count where the phase walkers fill the GPU), a 256-channel
     subset of configs[2] (Doppler + 2.4 Msps chain; the full 4096 channels take 0.6 s per step) and configs[0] (one CPU channel).
-    N = 8: configs[4], 32768 channels = 4096 per GPU."""
-    import bench_configs
+    Each runs tools/bench_configs.py in a process of its own (a clean CUDA context, and a failure there cannot cost the headline
+    line). N = 8: configs[4], 32768 channels = 4096 per GPU (run_c5)."""
     out = []
+    if world != 1:
+        return out
+    tool = os.path.join(ROOT, "tools", "bench_configs.py")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ""))
+    if not env["CUDA_VISIBLE_DEVICES"]:
+        env.pop("CUDA_VISIBLE_DEVICES")
 
-    class A:
-        pass
+    def run(config, extra):
+        cmd = [sys.executable, tool, "--config", config, "--device", str(local_rank)] + extra + (["--no-cpu"] if args.no_cpu else [])
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        lines = [x for x in proc.stdout.splitlines() if x.startswith("{")]
+        if proc.returncode != 0 or not lines:
+            raise RuntimeError("%s: rc %d: %s" % (" ".join(cmd[1:]), proc.returncode, proc.stderr[-300:]))
+        return json.loads(lines[-1])
 
-    if world == 1:
-        for n_ch, name in ((1024, "configs[3] gfsk_mod 1024 channels"), (16384, "configs[3] shape at 16384 channels (walkers saturated)")):
-            a = A()
-            a.channels, a.steps, a.warmup, a.device, a.no_cpu = n_ch, 50 if n_ch == 1024 else 10, 3, local_rank, args.no_cpu or n_ch != 1024
-            try:
-                r = bench_configs.bench_c4(a)
-                out.append({"name": name, "metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
-                            "steps": a.steps, "roofline_bound": "hbm", "roofline_achieved_gbs": r["roofline"]["achieved"],
-                            "roofline_peak_gbs": r["roofline"]["peak"], "roofline_frac": r["roofline"]["frac"],
-                            "cpu_value": r["cpu_baseline"]["value"] if r["cpu_baseline"] else None,
-                            "cpu_cores": r["cpu_baseline"]["cores"] if r["cpu_baseline"] else None,
-                            "gpu_launches": r["gpu_launches"], "note": r["roofline"]["note"]})
-            except Exception as e:  # a secondary line must not cost the headline
-                out.append({"name": name, "error": repr(e)[:200]})
-        a = A()
-        a.channels, a.steps, a.warmup, a.device, a.no_cpu, a.mode, a.fp32_peak = 256, 2, 3, local_rank, args.no_cpu, "exact", fp32_peak
+    for n_ch, steps, name in ((1024, 50, "configs[3] gfsk_mod 1024 channels"),
+                              (16384, 10, "configs[3] shape at 16384 channels (walkers saturated)")):
         try:
-            r = bench_configs.bench_c3(a)
-            out.append({"name": "configs[2] doppler + GMSK 2400 baud from 2.4 Msps, 256-channel subset of the 4096", "metric": r["metric"],
-                        "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"], "steps": a.steps,
-                        "roofline_bound": "fp32", "roofline_achieved_tflops": r["roofline"]["achieved"],
-                        "roofline_peak_tflops": r["roofline"]["peak"], "roofline_frac": r["roofline"]["frac"],
-                        "kernel_ms": r["roofline"]["kernel_ms"], "kernel_frac": r["roofline"]["kernel_frac"],
-                        "flop_per_sample": r["config"]["flop_per_sample"],
+            r = run("c4", ["--channels", str(n_ch), "--steps", str(steps)] + (["--no-cpu"] if n_ch != 1024 and not args.no_cpu else []))
+            out.append({"name": name, "metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
+                        "steps": steps, "roofline_bound": "hbm", "roofline_achieved_gbs": r["roofline"]["achieved"],
+                        "roofline_peak_gbs": r["roofline"]["peak"], "roofline_frac": r["roofline"]["frac"],
                         "cpu_value": r["cpu_baseline"]["value"] if r["cpu_baseline"] else None,
                         "cpu_cores": r["cpu_baseline"]["cores"] if r["cpu_baseline"] else None,
-                        "error_flags": r["error_flags"], "workload": r["config"]["workload"]})
+                        "gpu_launches": r["gpu_launches"], "note": r["roofline"]["note"]})
+        except Exception as e:  # a secondary line must not cost the headline
+            out.append({"name": name, "error": repr(e)[:300]})
+    try:
+        r = run("c3", ["--channels", "256", "--steps", "2", "--fp32-peak", "%.4f" % fp32_peak])
+        out.append({"name": "configs[2] doppler + GMSK 2400 baud from 2.4 Msps, 256-channel subset of the 4096", "metric": r["metric"],
+                    "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"], "steps": 2,
+                    "roofline_bound": "fp32", "roofline_achieved_tflops": r["roofline"]["achieved"],
+                    "roofline_peak_tflops": r["roofline"]["peak"], "roofline_frac": r["roofline"]["frac"],
+                    "kernel_ms": r["roofline"]["kernel_ms"], "kernel_frac": r["roofline"]["kernel_frac"],
+                    "flop_per_sample": r["config"]["flop_per_sample"],
+                    "cpu_value": r["cpu_baseline"]["value"] if r["cpu_baseline"] else None,
+                    "cpu_cores": r["cpu_baseline"]["cores"] if r["cpu_baseline"] else None,
+                    "error_flags": r["error_flags"], "workload": r["config"]["workload"]})
+    except Exception as e:
+        out.append({"name": "configs[2]", "error": repr(e)[:300]})
+    if not args.no_cpu:
+        try:
+            r = run("c1", [])
+            out.append({"name": "configs[0] one channel on one host core (reference CPU chain, strict build)", "metric": r["metric"],
+                        "value": r["value"], "unit": r["unit"], "cpu_cores": 1,
+                        "perf_fsk_modem_shape_value": r["shapes"]["perf_fsk_modem_48k_4800"]["msamples_per_s"],
+                        "seconds": r["shapes"]["c1_192k_9600"]["seconds"]})
         except Exception as e:
-            out.append({"name": "configs[2]", "error": repr(e)[:200]})
-        if not args.no_cpu:
-            try:
-                r = bench_configs.bench_c1(a)
-                out.append({"name": "configs[0] one channel on one host core (reference CPU chain, strict build)", "metric": r["metric"],
-                            "value": r["value"], "unit": r["unit"], "cpu_cores": 1,
-                            "perf_fsk_modem_shape_value": r["shapes"]["perf_fsk_modem_48k_4800"]["msamples_per_s"],
-                            "seconds": r["shapes"]["c1_192k_9600"]["seconds"]})
-            except Exception as e:
-                out.append({"name": "configs[0]", "error": repr(e)[:200]})
+            out.append({"name": "configs[0]", "error": repr(e)[:300]})
     return out
 
 

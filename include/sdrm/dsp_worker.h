@@ -3,10 +3,11 @@
  * it: one thread per RX session that takes blocks from its queue and runs
  *     [rx dump file] -> doppler_process_rx (optional) -> fsk_demod_process -> [demod file] -> [client socket].
  *
- * The reference's dsp_worker_create takes its parameters from protobuf (struct RxRequest) and libconfig
- * (struct server_config) objects, which belong to the control plane and are out of scope here; sdrm_dsp_worker_config
- * carries exactly the fields dsp_worker_create reads from them (src/dsp_worker.c:118-180), in the same units.
- * put / shutdown / destroy keep the reference's names and meaning.
+ * dsp_worker_create has the reference's signature (src/dsp_worker.h:22): struct RxRequest is the protobuf message of
+ * api_messages.h, struct server_config the layout of server_config.h. It is a thin layer over sdrm_dsp_worker_create, whose
+ * plain config struct carries exactly the fields the reference reads from those two objects (src/dsp_worker.c:118-180), in
+ * the same units, for hosts that have neither protobuf nor libconfig. put / shutdown / find / destroy keep the reference's
+ * names and meaning.
  */
 #ifndef SDRM_DSP_WORKER_H
 #define SDRM_DSP_WORKER_H
@@ -15,6 +16,9 @@
 #include <stdbool.h>
 #include <stddef.h>
 #include <stdint.h>
+
+#include "api_messages.h"
+#include "server_config.h"
 
 typedef struct dsp_worker_t dsp_worker;
 
@@ -47,9 +51,15 @@ typedef struct {
     uint16_t queue_size;
     bool blocking_queue;        /* rx_sdr_type == RX_SDR_TYPE_FILE */
     const char *base_path;
+    bool doppler_scaled_unsigned; /* the three scaled doppler values are the uint32 wire fields of struct DopplerSettings and
+                                     are divided as unsigned numbers, as the reference does (set by dsp_worker_create) */
 } sdrm_dsp_worker_config;
 
 int sdrm_dsp_worker_create(uint32_t id, int client_socket, const sdrm_dsp_worker_config *config, dsp_worker **result);
+
+/* the reference's entry point (src/dsp_worker.c:108-197): 0, -ENOMEM, -1 / the failing block's code; a GMSK request without
+ * fsk_settings is rejected with -1 (the reference dereferences the NULL pointer) */
+int dsp_worker_create(uint32_t id, int client_socket, struct server_config *config, struct RxRequest *req, dsp_worker **result);
 
 void dsp_worker_put(float complex *output, size_t output_len, dsp_worker *worker);
 

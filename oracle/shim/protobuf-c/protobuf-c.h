@@ -51,4 +51,13 @@ typedef struct ProtobufCMessage {
 
 typedef void (*ProtobufCClosure)(const ProtobufCMessage *, void *closure_data);
 
+/* protobuf-c run time call the reference's TCP server makes to print enum names (src/tcp_server.c:607,679); the product
+ * library implements it for the three enums of api.proto */
+typedef struct ProtobufCEnumValue {
+    const char *name;
+    const char *c_name;
+    int value;
+} ProtobufCEnumValue;
+const ProtobufCEnumValue *protobuf_c_enum_descriptor_get_value(const ProtobufCEnumDescriptor *desc, int value);
+
 #endif

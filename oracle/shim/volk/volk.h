@@ -31,6 +31,7 @@
 
 #include <complex.h>
 #include <math.h>
+#include <stdbool.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -156,6 +157,27 @@ static inline void volk_32f_s32f_convert_8i(int8_t *out, const float *in, const 
             out[i] = -128;
         } else {
             out[i] = (int8_t) rintf(r);
+        }
+    }
+}
+
+/* SDR sample formats of the PlutoSDR plugin (src/sdr/plutosdr.c:83,129), VOLK generic kernels:
+ * 16i -> 32f: (float) in / scalar;  32f -> 16i: in * scalar, saturated to [-32768, 32767], rintf */
+static inline void volk_16i_s32f_convert_32f(float *out, const int16_t *in, const float scalar, unsigned int num_points) {
+    for (unsigned int i = 0; i < num_points; i++) {
+        out[i] = (float) in[i] / scalar;
+    }
+}
+
+static inline void volk_32f_s32f_convert_16i(int16_t *out, const float *in, const float scalar, unsigned int num_points) {
+    for (unsigned int i = 0; i < num_points; i++) {
+        float r = in[i] * scalar;
+        if (r > 32767.0f) {
+            out[i] = 32767;
+        } else if (r < -32768.0f) {
+            out[i] = -32768;
+        } else {
+            out[i] = (int16_t) rintf(r);
         }
     }
 }

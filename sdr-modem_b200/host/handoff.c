@@ -9,6 +9,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include "../../include/sdrm/api.h"
 #include "../../include/sdrm/doppler.h"
 #include "../../include/sdrm/dsp_worker.h"
 #include "../../include/sdrm/fsk_demod.h"
@@ -284,6 +285,52 @@ static void *dsp_worker_callback(void *arg) {
     return NULL;
 }
 
+/* The reference's signature (src/dsp_worker.c:108-197): the fields it reads from the request and the server configuration,
+ * handed to sdrm_dsp_worker_create. */
+int dsp_worker_create(uint32_t id, int client_socket, struct server_config *server_config, struct RxRequest *req, dsp_worker **worker) {
+    if (server_config == NULL || req == NULL || worker == NULL) {
+        return -1;
+    }
+    sdrm_dsp_worker_config c;
+    memset(&c, 0, sizeof(c));
+    c.rx_center_freq = req->rx_center_freq;
+    c.rx_sampling_freq = req->rx_sampling_freq;
+    c.rx_dump_file = req->rx_dump_file != 0;
+    c.demod_gmsk = req->demod_type == MODEM_TYPE__GMSK;
+    c.demod_baud_rate = req->demod_baud_rate;
+    c.demod_decimation = req->demod_decimation;
+    if (c.demod_gmsk) {
+        if (req->fsk_settings == NULL) {
+            SDRM_LOG_ERROR("[%d] missing fsk settings", id);
+            return -1;
+        }
+        c.demod_fsk_deviation = req->fsk_settings->demod_fsk_deviation;
+        c.demod_fsk_transition_width = req->fsk_settings->demod_fsk_transition_width;
+        c.demod_fsk_use_dc_block = req->fsk_settings->demod_fsk_use_dc_block != 0;
+    }
+    c.demod_destination = (int) req->demod_destination;
+    if (req->doppler != NULL) {
+        if (req->doppler->n_tle < 3) {
+            SDRM_LOG_ERROR("[%d] unable to create doppler correction block", id);
+            return -1;
+        }
+        c.has_doppler = true;
+        api_utils_convert_tle(req->doppler->tle, c.doppler_tle);
+        /* the scaled integers travel as uint32 on the wire and were written from signed values (api.proto: "degrees times
+         * 10^6"); the reference divides the unsigned value, so does this */
+        c.doppler_latitude = (int32_t) req->doppler->latitude;
+        c.doppler_longitude = (int32_t) req->doppler->longitude;
+        c.doppler_altitude = (int32_t) req->doppler->altitude;
+        c.doppler_scaled_unsigned = true;
+    }
+    c.file_start_time_seconds = req->file_settings != NULL ? (int64_t) req->file_settings->start_time_seconds : 0;
+    c.buffer_size = server_config->buffer_size;
+    c.queue_size = server_config->queue_size;
+    c.blocking_queue = server_config->rx_sdr_type == RX_SDR_TYPE_FILE;
+    c.base_path = server_config->base_path;
+    return sdrm_dsp_worker_create(id, client_socket, &c, worker);
+}
+
 int sdrm_dsp_worker_create(uint32_t id, int client_socket, const sdrm_dsp_worker_config *config, dsp_worker **out) {
     if (config == NULL || out == NULL) {
         return -1;
@@ -299,8 +346,16 @@ int sdrm_dsp_worker_create(uint32_t id, int client_socket, const sdrm_dsp_worker
         char tle[3][80];
         memcpy(tle, config->doppler_tle, sizeof(tle));
         /* same scalings as src/dsp_worker.c:130 */
-        code = doppler_create(config->doppler_latitude / 10E6, config->doppler_longitude / 10E6, config->doppler_altitude / 10E3,
-                              config->rx_sampling_freq, config->rx_center_freq, 0, (time_t) config->file_start_time_seconds,
+        double latitude = config->doppler_latitude / 10E6;
+        double longitude = config->doppler_longitude / 10E6;
+        double altitude = config->doppler_altitude / 10E3;
+        if (config->doppler_scaled_unsigned) {
+            /* the wire fields are uint32 and the reference divides them as such (src/dsp_worker.c:130) */
+            latitude = (uint32_t) config->doppler_latitude / 10E6;
+            longitude = (uint32_t) config->doppler_longitude / 10E6;
+            altitude = (uint32_t) config->doppler_altitude / 10E3;
+        }
+        code = doppler_create(latitude, longitude, altitude, config->rx_sampling_freq, config->rx_center_freq, 0, (time_t) config->file_start_time_seconds,
                               config->buffer_size, tle, &result->dopp);
         if (code != 0) {
             SDRM_LOG_ERROR("[%d] unable to create doppler correction block", id);

@@ -23,6 +23,9 @@ static inline int sdrm_cuda_code(cudaError_t err, const char *what) {
         return 0;
     }
     SDRM_LOG_ERROR("cuda failure in %s: %s", what, cudaGetErrorString(err));
+    /* a failed runtime call also parks its code as the thread's "last error", where the cudaGetLastError() check behind the
+     * next kernel launch of an unrelated handle would find it: it has been reported here, clear it */
+    (void) cudaGetLastError();
     return err == cudaErrorMemoryAllocation ? -ENOMEM : -EIO;
 }
 

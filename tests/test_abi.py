@@ -19,8 +19,11 @@ def declared_functions(path):
     text = open(path).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     text = re.sub(r"//[^\n]*", "", text)
+    text = text.replace("\\\n", " ")  # continuation lines belong to their #define
     text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
-    text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+    text = re.sub(r"__attribute__\s*\(\(.*?\)\)", "", text)
+    # struct and enum bodies (members may be function pointers) hold no function declarations
+    text = re.sub(r"(?:typedef\s+)?(?:struct|enum)\s*\w*\s*\{[^{}]*\}\s*\w*\s*;", "", text, flags=re.S)
     names = []
     for stmt in text.split(";"):
         m = re.search(r"(\w+)\s*\(", stmt)

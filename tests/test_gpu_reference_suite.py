@@ -16,7 +16,13 @@ TESTS = ["test_lpf", "test_lpf_taps", "test_quadrature_demod", "test_dc_blocker"
          "test_mmse_fir_interpolator", "test_sig_source", "test_gaussian_taps", "test_interp_fir_filter",
          "test_frequency_modulator", "test_gfsk_mod", "test_fsk_demod", "test_doppler", "test_queue",
          # a caller of the path: the reference's file SDR plugin (src/sdr/file_source.c) on the product's sig_source
-         "test_file_source"]
+         "test_file_source",
+         # dsp_worker_create with the reference's signature; requests built by the reference's test/utils.c through the
+         # product's protobuf codec (make -C oracle server-tests)
+         "test_dsp_worker",
+         # the reference's whole control plane, unmodified (src/tcp_server.c, sdr_worker.c, server_config.c, SDR plugins, its
+         # test client and SDR mocks), on top of the product library: RX and TX sessions over real sockets
+         "test_tcp_server"]
 
 
 @pytest.mark.parametrize("name", TESTS)

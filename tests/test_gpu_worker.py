@@ -20,7 +20,8 @@ class WorkerConfig(C.Structure):
                 ("demod_fsk_use_dc_block", C.c_bool), ("demod_destination", C.c_int), ("has_doppler", C.c_bool),
                 ("doppler_tle", (C.c_char * 80) * 3), ("doppler_latitude", C.c_int32), ("doppler_longitude", C.c_int32),
                 ("doppler_altitude", C.c_int32), ("file_start_time_seconds", C.c_int64), ("buffer_size", C.c_uint32),
-                ("queue_size", C.c_uint16), ("blocking_queue", C.c_bool), ("base_path", C.c_char_p)]
+                ("queue_size", C.c_uint16), ("blocking_queue", C.c_bool), ("base_path", C.c_char_p),
+                ("doppler_scaled_unsigned", C.c_bool)]
 
 
 def setup_lib(lib):

@@ -332,7 +332,12 @@ def main():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--mode", default="exact", choices=["exact", "fast"], help="c3: arithmetic mode of the demodulator")
     p.add_argument("--device", type=int, default=0)
+    p.add_argument("--fp32-peak", type=float, default=None, dest="fp32_peak",
+                   help="measured FMA peak in TFLOP/s to quote the fp32 roofline against (bench.py passes its own measurement)")
     args = p.parse_args()
+    if args.config not in ("c1",):
+        import torch
+        torch.cuda.set_device(args.device)
     if args.config == "c4":
         args.channels = args.channels or 1024
         args.steps = args.steps or 50
