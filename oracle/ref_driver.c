@@ -63,7 +63,12 @@ long ref_fsk_chain_run(uint64_t fs, uint32_t baud, int64_t deviation, uint8_t de
     if (use_dc) {
         if (dc_blocker_create((int) ceilf(sps * 32), &dc) != 0) goto done;
     }
-    if (clock_mm_create(sps, (sps * (float) M_PI) / 100, 0.5f, 0.5f / 8.0f, 0.01f, max_len, &clock) != 0) goto done;
+    /* The reference sizes the clock's working buffer as output_len + 8 floats and copies the whole input behind the carried
+     * samples (clock_recovery_mm.c:57,87): with decimation 1 and a full-size call, more than 8 carried samples (any chain with
+     * more than ~6 samples per symbol) write past the allocation. fsk_demod_create passes the same length, so the reference
+     * has this overflow itself; here the buffer gets head room so that the checker does not corrupt its heap. The length only
+     * bounds the call size and the symbol count per call, neither of which is reached: results are unchanged. */
+    if (clock_mm_create(sps, (sps * (float) M_PI) / 100, 0.5f, 0.5f / 8.0f, 0.01f, (size_t) max_len + 256, &clock) != 0) goto done;
 
     size_t produced = 0;
     size_t lpf2_total = 0;

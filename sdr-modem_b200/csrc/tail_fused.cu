@@ -136,8 +136,11 @@ __device__ __forceinline__ float branchless_clip(float x, float clip) {
     return __fmul_rn(0.5f, __fsub_rn(fabsf(__fadd_rn(x, clip)), fabsf(__fsub_rn(x, clip))));
 }
 
-__device__ __forceinline__ float dot_step(bool fast, float acc, float v, float t) {
-    return fast ? __fmaf_rn(v, t, acc) : __fadd_rn(acc, __fmul_rn(v, t));
+// the arithmetic mode is a template parameter: as a run-time flag every tap of the interpolator was issued in both forms (an
+// FFMA, then a predicated FADD over the same register) inside the loop's dependent chain
+template <bool FAST>
+__device__ __forceinline__ float dot_step(float acc, float v, float t) {
+    return FAST ? __fmaf_rn(v, t, acc) : __fadd_rn(acc, __fmul_rn(v, t));
 }
 
 // sum / L, correctly rounded, for a constant L with rcp = RN(1/L): Markstein corrections of q0 = RN(sum * rcp).
@@ -405,7 +408,7 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
 
 // PROD producer warps (4 moving averages, or 1 plain copier when the dc blocker is off) + 1 clock warp.
 // All per-channel arrays are padded to a multiple of 32 channels, so every lane owns real memory.
-template <int PROD, int DIVSTEPS>
+template <int PROD, int DIVSTEPS, bool FAST>
 __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_tail_args a) {
     extern __shared__ __align__(128) float smem[];
     Layout s;
@@ -552,12 +555,12 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                 // the accumulator (+0, or already NaN) unchanged.
                 const int lead = ii & 3;
                 float acc = 0.0f;
-                acc = dot_step(a.fast, acc, lead >= 3 ? v[0] : 0.0f, 0.0f);
-                acc = dot_step(a.fast, acc, lead >= 2 ? v[1] : 0.0f, 0.0f);
-                acc = dot_step(a.fast, acc, lead >= 1 ? v[2] : 0.0f, 0.0f);
+                acc = dot_step<FAST>(acc, lead >= 3 ? v[0] : 0.0f, 0.0f);
+                acc = dot_step<FAST>(acc, lead >= 2 ? v[1] : 0.0f, 0.0f);
+                acc = dot_step<FAST>(acc, lead >= 1 ? v[2] : 0.0f, 0.0f);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    acc = dot_step(a.fast, acc, v[3 + k], tp[7 - k]);
+                    acc = dot_step<FAST>(acc, v[3 + k], tp[7 - k]);
                 }
                 const bool nan = isnan(acc);  // clock_recovery_mm.c:107-113: output 0, skip the loop update
                 const float out = nan ? 0.0f : acc;
@@ -687,12 +690,19 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
     const size_t floats = (size_t) kTapsFloats + (size_t) (args->ring_slots + kMirror) * 32 + (size_t) (prod - 1) * 2 * kTile + 2 * kTile +
                           (size_t) prod * 2 * kTile + 2 * kTile;
     const size_t smem = floats * sizeof(float) + (size_t) prod * 2 * sizeof(uint64_t);
-    void (*kernel)(const sdrm_tail_args) =
-        !has_dc ? demod_tail_kernel<1, 2>
-                : (args->div_steps == 1 ? demod_tail_kernel<4, 1> : (args->div_steps == 2 ? demod_tail_kernel<4, 2> : demod_tail_kernel<4, 0>));
+    void (*kernel)(const sdrm_tail_args);
+    if (args->fast) {
+        kernel = !has_dc ? demod_tail_kernel<1, 2, true>
+                         : (args->div_steps == 1 ? demod_tail_kernel<4, 1, true>
+                                                 : (args->div_steps == 2 ? demod_tail_kernel<4, 2, true> : demod_tail_kernel<4, 0, true>));
+    } else {
+        kernel = !has_dc ? demod_tail_kernel<1, 2, false>
+                         : (args->div_steps == 1 ? demod_tail_kernel<4, 1, false>
+                                                 : (args->div_steps == 2 ? demod_tail_kernel<4, 2, false> : demod_tail_kernel<4, 0, false>));
+    }
     // function attributes once per (variant, device), sized for the largest ring (fir.cu does the same): not per launch
-    static std::atomic<bool> configured[4][64];
-    const int variant = !has_dc ? 3 : (args->div_steps == 1 ? 1 : (args->div_steps == 2 ? 2 : 0));
+    static std::atomic<bool> configured[8][64];
+    const int variant = (!has_dc ? 3 : (args->div_steps == 1 ? 1 : (args->div_steps == 2 ? 2 : 0))) + (args->fast ? 4 : 0);
     int device = 0;
     cudaGetDevice(&device);
     cudaError_t err = cudaSuccess;

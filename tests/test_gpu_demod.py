@@ -16,7 +16,15 @@ pytestmark = pytest.mark.gpu
 
 
 def oracle_chain(port, args, iq, chunk):
-    return port.FskDemod(*args, chunk).run(iq, chunk)
+    """The expected result: our C restatement (oracle/sdrm_oracle.c) and, wherever the reference build travelled with the
+    repo (oracle/_ref), the reference's own sources on the same input, which must agree with it bit for bit: every
+    comparison of this file is therefore a comparison with the reference itself, on the machine the GPU tests run on."""
+    hard, soft = port.FskDemod(*args, chunk).run(iq, chunk)
+    from oracle import ref
+    if ref.available():
+        r = ref.fsk_chain(*args, iq, chunk)
+        assert same_bits(hard, r["hard"]) and same_bits(soft, r["soft"]), "oracle port differs from the reference build"
+    return hard, soft
 
 
 def gpu_chain(sdrm, args, iq_channels, chunk, **kw):
