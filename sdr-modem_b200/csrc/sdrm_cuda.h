@@ -137,7 +137,7 @@ typedef struct {
     int div_steps;       /* sdrm_division_steps(dc_length): corrections the branch-free division needs (1 or 2); 0 = use __fdiv_rn */
     float *delay;        /* float [4][n_groups][dc_length][32] (last L inputs of each moving average), then
                             float [n_groups][dx_length][32] (group delay line); zero-initialised */
-    int dx_length;       /* >= 2 * dc_length - 2 + 256: the pipeline's first stage writes ahead of its last */
+    int dx_length;       /* >= 2 * dc_length - 2 + 8 pipeline steps (of 32 or 64 rows): the first stage writes ahead of the last */
     float *sums;         /* float [4][delay_stride] */
     size_t delay_stride; /* channels rounded up (row pitch of delay, sums and carry) */
     int pos_l;           /* rows processed so far modulo dc_length */

@@ -233,40 +233,41 @@ struct Cursors {
     int dx_load;   // group delay line: where the last stage reads x[n - (2L - 2)]
 };
 
-__device__ __forceinline__ int advance(int pos, int len) {
-    pos += kBlockRows;
+__device__ __forceinline__ int advance(int pos, int len, int rows) {
+    pos += rows;
     return pos >= len ? pos - len : pos;
 }
 
+template <int SB>
 __device__ __forceinline__ Cursors next_block(const sdrm_tail_args &a, const Cursors &c) {
     Cursors n;
-    n.line = advance(c.line, a.dc_length);
-    n.dx_store = advance(c.dx_store, a.dx_length);
-    n.dx_load = advance(c.dx_load, a.dx_length);
+    n.line = advance(c.line, a.dc_length, SB * kBlockRows);
+    n.dx_store = advance(c.dx_store, a.dx_length, SB * kBlockRows);
+    n.dx_load = advance(c.dx_load, a.dx_length, SB * kBlockRows);
     return n;
 }
 
-template <int PROD>
+template <int PROD, int SB>
 __device__ __forceinline__ void fetch_block(const sdrm_tail_args &a, const Layout &s, const Arrays &g, int warp, int lane, int b,
                                             const Cursors &c) {
     if (!elect_one()) {
         return;
     }
     const bool has_dc = PROD == 4;
-    const int row0 = b * kBlockRows;
-    const int nr = min(kBlockRows, a.n_rows - row0);
+    const int row0 = b * SB * kBlockRows;
+    const int nr = min(SB * kBlockRows, a.n_rows - row0);
     const int parity = b & 1;
     uint64_t *bar = s.bars + warp * 2 + parity;
     const int copies = (warp == 0 ? 1 : 0) + (has_dc ? 1 : 0) + (has_dc && warp == PROD - 1 ? 1 : 0);
     mbar_expect_tx(bar, (uint32_t) (copies * nr * kRowBytes));
     if (warp == 0) {
         const int first = (int) ((a.head + row0) & (a.ring_rows - 1));
-        bulk_load_rows(s.rows + parity * kTile, g.rows, first, nr, a.ring_rows, bar);
+        bulk_load_rows(s.rows + parity * SB * kTile, g.rows, first, nr, a.ring_rows, bar);
     }
     if (has_dc) {
-        bulk_load_rows(s.line + (warp * 2 + parity) * kTile, g.line, c.line, nr, a.dc_length, bar);
+        bulk_load_rows(s.line + (warp * 2 + parity) * SB * kTile, g.line, c.line, nr, a.dc_length, bar);
         if (warp == PROD - 1) {
-            bulk_load_rows(s.dx + parity * kTile, g.dx, c.dx_load, nr, a.dx_length, bar);
+            bulk_load_rows(s.dx + parity * SB * kTile, g.dx, c.dx_load, nr, a.dx_length, bar);
         }
     }
 }
@@ -283,14 +284,14 @@ __device__ __forceinline__ void ring_put(float *ring_lane, int pos, int ring_slo
 //   moving average  y = in - in[n-L] + y_prev ; out = y / L                           (dc_blocker.c:52-64)
 //   last stage      x[n-(2L-2)] - y4 appended to the clock's sample ring              (dc_blocker.c:110-114)
 // FULL blocks carry no per-row guards, so the 32 rows form one basic block that ptxas interleaves freely.
-template <int PROD, bool FULL, int DIVSTEPS>
-__device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Layout &s, const Arrays &g, int warp, int lane, int b,
-                                               int nr, const Cursors &c, float &sum, float rcp) {
+template <int PROD, int SB, bool FULL, int DIVSTEPS>
+__device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const Layout &s, int warp, int lane, int b, int h, int nr,
+                                               float &sum, float rcp) {
     const bool has_dc = PROD == 4;
     const int ring_mask = a.ring_slots - 1;
-    const int row0 = b * kBlockRows;
+    const int row0 = (b * SB + h) * kBlockRows;  // h: which 32-row block of the step's SB
     const int parity = b & 1;
-    const float *in_tile = warp == 0 ? s.rows + parity * kTile : s.pipe + ((warp - 1) * 2 + parity) * kTile;
+    const float *in_tile = (warp == 0 ? s.rows + parity * SB * kTile : s.pipe + ((warp - 1) * 2 + parity) * SB * kTile) + h * kTile;
     const float *src = in_tile + lane;
     // this block's 32 rows of the clock's ring: aligned to the block size, so they never wrap (ring_slots is a power of two)
     float *ring_block = s.ring + lane + (row0 & ring_mask) * 32;
@@ -312,19 +313,9 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
         }
         return;
     }
-    // the block's own inputs replace the ones it is about to consume: the input tile goes back to the stage's delay line
-    // (slots are distinct: L >= 32) and, for the first stage, to the group delay line, which is 2L - 2 + 256 slots long
-    // so that these writes never reach what the last stage still has to read
-    if (elect_one()) {  // always the same lane for the full mask: it owns the warp's bulk groups
-        bulk_store_rows(g.line, in_tile, c.line, nr, a.dc_length);
-        if (warp == 0) {
-            bulk_store_rows(g.dx, in_tile, c.dx_store, nr, a.dx_length);
-        }
-        bulk_commit();
-    }
 
     const float length_f = (float) a.dc_length;
-    const float *delayed = s.line + (warp * 2 + parity) * kTile + lane;
+    const float *delayed = s.line + (warp * 2 + parity) * SB * kTile + h * kTile + lane;
     float y[kBlockRows];
 #pragma unroll
     for (int r = 0; r < kBlockRows; r++) {
@@ -343,7 +334,7 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
     // between the stores at the end (they were: LDS, FADD, STS one after the other, 35 cycles a row).
     float xv[kBlockRows];
     if (warp == PROD - 1) {
-        const float *xd = s.dx + parity * kTile + lane;
+        const float *xd = s.dx + parity * SB * kTile + h * kTile + lane;
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
@@ -377,7 +368,7 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
         }
     }
     if (warp < PROD - 1) {
-        float *dst = s.pipe + (warp * 2 + parity) * kTile + lane;
+        float *dst = s.pipe + (warp * 2 + parity) * SB * kTile + h * kTile + lane;
 #pragma unroll
         for (int r = 0; r < kBlockRows; r++) {
             if (FULL || r < nr) {
@@ -401,24 +392,26 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
             }
         }
     }
-    if (warp < PROD - 1) {
-        fence_async_smem();  // the next stage sends this tile to its delay line with a bulk store
-    }
 }
 
 // PROD producer warps (4 moving averages, or 1 plain copier when the dc blocker is off) + 1 clock warp.
 // All per-channel arrays are padded to a multiple of 32 channels, so every lane owns real memory.
-template <int PROD, int DIVSTEPS, bool FAST>
+// SB = 32-row blocks per pipeline step. A step has fixed costs that do not depend on its size (issuing and retiring the bulk
+// copies, the fences, the step barrier: about half of a 32-row step), and the clock warp loses fewer trips to lanes that sit
+// at different symbol phases when more rows arrive at once, so two blocks per step are used wherever shared memory and the
+// delay-line lengths allow it (8 KB tiles).
+template <int PROD, int DIVSTEPS, bool FAST, int SB>
 __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_tail_args a) {
     extern __shared__ __align__(128) float smem[];
     Layout s;
     s.taps = smem;
     s.ring = s.taps + kTapsFloats;
     s.pipe = s.ring + (size_t) (a.ring_slots + kMirror) * 32;
-    s.rows = s.pipe + (PROD - 1) * 2 * kTile;
-    s.line = s.rows + 2 * kTile;
-    s.dx = s.line + PROD * 2 * kTile;
-    s.bars = reinterpret_cast<uint64_t *>(s.dx + 2 * kTile);
+    s.rows = s.pipe + (PROD - 1) * 2 * SB * kTile;
+    s.line = s.rows + 2 * SB * kTile;
+    s.dx = s.line + PROD * 2 * SB * kTile;
+    s.bars = reinterpret_cast<uint64_t *>(s.dx + 2 * SB * kTile);
+    constexpr int kStepRows = SB * kBlockRows;
     const int ring_mask = a.ring_slots - 1;
     for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) {
         s.taps[i] = a.mmse_taps[i];
@@ -443,7 +436,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
 
     const sdrm_clock_state st = a.state[ch];
     int history = st.history;
-    const int max_carry = a.ring_slots - 2 * kBlockRows - kGuard;
+    const int max_carry = a.ring_slots - 2 * kStepRows - kGuard;
     if (history > max_carry) {  // cannot happen unless a previous call already raised the error flag
         history = max_carry;
     }
@@ -454,7 +447,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
             ring_put(ring_lane, (k - history) & ring_mask, a.ring_slots, a.carry[(size_t) k * a.delay_stride + ch]);
         }
     }
-    const int n_blocks = (a.n_rows + kBlockRows - 1) / kBlockRows;
+    const int n_blocks = (a.n_rows + kStepRows - 1) / kStepRows;  // steps' worth of rows ("blocks" of SB x 32 rows below)
     const int n_steps = n_blocks + PROD;
 
     // producer state
@@ -474,8 +467,8 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
     cur.dx_store = has_dc ? (int) (a.pos_x % a.dx_length) : 0;
     cur.dx_load = has_dc ? (int) ((a.pos_x + a.dx_length - (2 * a.dc_length - 2)) % a.dx_length) : 0;
     // a block's delay-line slots may be fetched one block ahead only if the previous block does not write them
-    const bool lookahead = !has_dc || a.dc_length >= 2 * kBlockRows;
-    const int store_slack = has_dc ? max(0, min(2, (a.dc_length - 2 * kBlockRows) / kBlockRows)) : 0;
+    const bool lookahead = !has_dc || a.dc_length >= 2 * kStepRows;
+    const int store_slack = has_dc ? max(0, min(2, (a.dc_length - 2 * kStepRows) / kStepRows)) : 0;
 
     // clock state (warp PROD)
     float *soft = a.soft_out != nullptr ? a.soft_out + (size_t) ch * a.out_stride : nullptr;
@@ -497,23 +490,44 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
         if (warp < PROD) {
             const int b = t - warp;
             if (b >= 0 && b < n_blocks) {
-                const int nr = min(kBlockRows, a.n_rows - b * kBlockRows);
-                const Cursors nxt = next_block(a, cur);
+                const int nr = min(kStepRows, a.n_rows - b * kStepRows);
+                const Cursors nxt = next_block<SB>(a, cur);
                 if (b == 0 || !lookahead) {
-                    fetch_block<PROD>(a, s, arrays, warp, lane, b, cur);
+                    fetch_block<PROD, SB>(a, s, arrays, warp, lane, b, cur);
                 }
                 if (lookahead && b + 1 < n_blocks) {
-                    fetch_block<PROD>(a, s, arrays, warp, lane, b + 1, nxt);
+                    fetch_block<PROD, SB>(a, s, arrays, warp, lane, b + 1, nxt);
                 }
                 mbar_wait(s.bars + warp * 2 + (b & 1), (uint32_t) ((b >> 1) & 1));
-                if (nr == kBlockRows) {
-                    producer_block<PROD, true, DIVSTEPS>(a, s, arrays, warp, lane, b, nr, cur, sum, rcp);
-                } else {
-                    producer_block<PROD, false, DIVSTEPS>(a, s, arrays, warp, lane, b, nr, cur, sum, rcp);
+                if (has_dc) {
+                    // the step's own inputs replace the ones it is about to consume: the input tile goes back to the stage's
+                    // delay line (slots are distinct: L >= the step's rows) and, for the first stage, to the group delay line,
+                    // which is long enough that these writes never reach what the last stage still has to read
+                    if (elect_one()) {  // always the same lane for the full mask: it owns the warp's bulk groups
+                        const float *in_tile =
+                            warp == 0 ? s.rows + (b & 1) * SB * kTile : s.pipe + ((warp - 1) * 2 + (b & 1)) * SB * kTile;
+                        bulk_store_rows(arrays.line, in_tile, cur.line, nr, a.dc_length);
+                        if (warp == 0) {
+                            bulk_store_rows(arrays.dx, in_tile, cur.dx_store, nr, a.dx_length);
+                        }
+                        bulk_commit();
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < SB; h++) {
+                    const int nr_h = nr - h * kBlockRows;
+                    if (nr_h >= kBlockRows) {
+                        producer_block<PROD, SB, true, DIVSTEPS>(a, s, warp, lane, b, h, kBlockRows, sum, rcp);
+                    } else if (nr_h > 0) {
+                        producer_block<PROD, SB, false, DIVSTEPS>(a, s, warp, lane, b, h, nr_h, sum, rcp);
+                    }
+                }
+                if (has_dc && warp < PROD - 1) {
+                    fence_async_smem();  // the next stage sends this tile to its delay line with a bulk store
                 }
                 cur = nxt;
-                // this block's delay-line stores are done before the step ends: their source tile is recycled two steps
-                // later and the lines are read again at the earliest one block later
+                // this step's delay-line stores are done before the step ends: their source tile is recycled two steps
+                // later and the lines are read again at the earliest one step later
                 if (elect_one()) {  // always the same lane for the full mask: it owns the warp's bulk groups
                     bulk_wait_step(store_slack);
                 }
@@ -521,7 +535,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
         } else {
             // Mueller & Mueller loop over everything the last producer finished before this step
             const int done_blocks = t - PROD + 1;
-            const int avail = history + (done_blocks <= 0 ? 0 : min(a.n_rows, done_blocks * kBlockRows));
+            const int avail = history + (done_blocks <= 0 ? 0 : min(a.n_rows, done_blocks * kStepRows));
             // The body is branch-free: the reference's three data-dependent paths (leading zero taps, NaN output, loop
             // update) are computed side by side and selected, so that lanes in different situations stay converged and the
             // iteration is one dependent chain of ~40 operations instead of a sequence of divergent regions.
@@ -529,7 +543,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
             // idle lanes must then be kept away from ring rows that are still being written, and the extra select on the
             // window address costs more than the uniform control flow saves.)
             while (run_clock && ii >= 0 && ii + 7 < avail && oo < a.max_out) {
-                if (avail + kBlockRows - (ii - 3) > a.ring_slots) {  // the lane fell behind its ring (pathological input)
+                if (avail + kStepRows - (ii - 3) > a.ring_slots) {  // the lane fell behind its ring (pathological input)
                     overflow = true;
                     break;
                 }
@@ -687,31 +701,48 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
     cudaStream_t stream = (cudaStream_t) stream_ptr;
     const int blocks = (args->n_ch + 31) / 32;
     const int prod = has_dc ? 4 : 1;
-    const size_t floats = (size_t) kTapsFloats + (size_t) (args->ring_slots + kMirror) * 32 + (size_t) (prod - 1) * 2 * kTile + 2 * kTile +
-                          (size_t) prod * 2 * kTile + 2 * kTile;
-    const size_t smem = floats * sizeof(float) + (size_t) prod * 2 * sizeof(uint64_t);
-    void (*kernel)(const sdrm_tail_args);
-    if (args->fast) {
-        kernel = !has_dc ? demod_tail_kernel<1, 2, true>
-                         : (args->div_steps == 1 ? demod_tail_kernel<4, 1, true>
-                                                 : (args->div_steps == 2 ? demod_tail_kernel<4, 2, true> : demod_tail_kernel<4, 0, true>));
-    } else {
-        kernel = !has_dc ? demod_tail_kernel<1, 2, false>
-                         : (args->div_steps == 1 ? demod_tail_kernel<4, 1, false>
-                                                 : (args->div_steps == 2 ? demod_tail_kernel<4, 2, false> : demod_tail_kernel<4, 0, false>));
-    }
-    // function attributes once per (variant, device), sized for the largest ring (fir.cu does the same): not per launch
-    static std::atomic<bool> configured[8][64];
-    const int variant = (!has_dc ? 3 : (args->div_steps == 1 ? 1 : (args->div_steps == 2 ? 2 : 0))) + (args->fast ? 4 : 0);
     int device = 0;
     cudaGetDevice(&device);
-    cudaError_t err = cudaSuccess;
-    if (device < 0 || device >= 64 || !configured[variant][device].load(std::memory_order_acquire)) {
-        int optin = 0;
-        err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-        if (err == cudaSuccess) {
-            err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    int optin = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (err != cudaSuccess) {
+        return -(int) err - 1000;
+    }
+    // two 32-row blocks per step where everything is long enough for 64-row steps and the tiles fit in shared memory
+    int sb = 2;
+    size_t smem = 0;
+    for (; sb >= 1; sb--) {
+        const size_t tiles = (size_t) (prod - 1) * 2 + 2 + (size_t) prod * 2 + 2;
+        const size_t floats = (size_t) kTapsFloats + (size_t) (args->ring_slots + kMirror) * 32 + tiles * sb * kTile;
+        smem = floats * sizeof(float) + (size_t) prod * 2 * sizeof(uint64_t);
+        const int step_rows = sb * kBlockRows;
+        const bool fits = smem <= (size_t) optin && args->ring_slots >= 2 * step_rows + kGuard + 16 &&
+                          (!has_dc || (args->dc_length >= step_rows && args->dx_length >= 2 * args->dc_length - 2 + 8 * step_rows));
+        if (fits) {
+            break;
         }
+    }
+    if (sb < 1) {
+        return -22;
+    }
+    const int steps_idx = !has_dc ? 3 : (args->div_steps == 1 ? 1 : (args->div_steps == 2 ? 2 : 0));
+    typedef void (*tail_kernel_t)(const sdrm_tail_args);
+    // [fast][division variant][blocks per step - 1]
+    static const tail_kernel_t kernels[2][4][2] = {
+        {{demod_tail_kernel<4, 0, false, 1>, demod_tail_kernel<4, 0, false, 2>},
+         {demod_tail_kernel<4, 1, false, 1>, demod_tail_kernel<4, 1, false, 2>},
+         {demod_tail_kernel<4, 2, false, 1>, demod_tail_kernel<4, 2, false, 2>},
+         {demod_tail_kernel<1, 2, false, 1>, demod_tail_kernel<1, 2, false, 2>}},
+        {{demod_tail_kernel<4, 0, true, 1>, demod_tail_kernel<4, 0, true, 2>},
+         {demod_tail_kernel<4, 1, true, 1>, demod_tail_kernel<4, 1, true, 2>},
+         {demod_tail_kernel<4, 2, true, 1>, demod_tail_kernel<4, 2, true, 2>},
+         {demod_tail_kernel<1, 2, true, 1>, demod_tail_kernel<1, 2, true, 2>}}};
+    tail_kernel_t kernel = kernels[args->fast ? 1 : 0][steps_idx][sb - 1];
+    // function attributes once per (variant, device), sized for the largest ring (fir.cu does the same): not per launch
+    static std::atomic<bool> configured[16][64];
+    const int variant = ((args->fast ? 4 : 0) + steps_idx) * 2 + (sb - 1);
+    if (device < 0 || device >= 64 || !configured[variant][device].load(std::memory_order_acquire)) {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
         if (err != cudaSuccess) {
             return -(int) err - 1000;
         }

@@ -215,7 +215,9 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
             code = -1;
             goto fail;
         }
-        b->dx_len = 2 * b->dc_len - 2 + 256;
+        /* group delay line: 2L - 2 rows of delay + the rows the pipeline's first stage writes ahead of its last (4 steps of up
+         * to 64 rows), with the same again as head room */
+        b->dx_len = 2 * b->dc_len - 2 + 512;
         b->div_steps = sdrm_division_steps(b->dc_len);
         code = sdrm_dev_zalloc((void **) &b->d_delay, ((size_t) 4 * b->dc_len + b->dx_len) * b->n_ch_pad * sizeof(float));
         if (code != 0) goto fail;
@@ -243,8 +245,8 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
         free(init);
         if (code != 0) goto fail;
     }
-    /* per-lane shared-memory ring of the fused tail: one symbol step + one 32-row block + slack, power of two */
-    b->ring_slots = (int) sdrm_next_pow2((uint64_t) ceilf(sps * 1.01f) + 8 + 2 * 32 + 16 + 8);
+    /* per-lane shared-memory ring of the fused tail: one symbol step + two pipeline steps of 64 rows + slack, power of two */
+    b->ring_slots = (int) sdrm_next_pow2((uint64_t) ceilf(sps * 1.01f) + 8 + 2 * 64 + 16 + 8);
     if (b->ring_slots < 128) {
         b->ring_slots = 128;
     }
