@@ -11,7 +11,14 @@
 //               warp 2  MA2 on block t-2
 //               warp 3  MA3 on block t-3    -> x[n-(2L-2)] - y4, appended to the per-lane sample ring in shared memory
 //               warp 4  clock recovery over everything complete, interpolating straight out of that ring
-//     __syncthreads()
+//     barrier among the four producer warps (bar.sync 1)
+//
+// The clock warp is NOT part of that step barrier: a step of the producers costs about the same every time, the clock's
+// cost varies from step to step (lanes sit at different symbol phases, so the same number of new rows is a different number
+// of trips of the warp), and in lock step every step cost the maximum of the two. The sample ring is therefore a proper
+// producer / consumer queue of step-sized blocks with one "full" and one "empty" mbarrier per block slot: the last producer
+// waits for a slot to be released before it overwrites it and signals it full, the clock warp takes whatever is complete and
+// releases the blocks every active lane has moved past. The two sides then cost max(sum, sum) instead of sum(max).
 //
 // Data movement is all TMA bulk copies (cp.async.bulk). Every global array the loop touches is blocked by groups of 32
 // channels ([group][row][32]), so a block of 32 rows of one group is 4 KB of contiguous memory and moves with ONE copy
@@ -69,6 +76,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void producers_barrier(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
 // Rows [first, first + n) of a circular array of `len` rows of 32 channels (128 bytes each, contiguous) <-> a tile in
 // shared memory: one TMA bulk copy, or two when the span wraps around the end of the array.
@@ -198,7 +211,9 @@ struct Layout {
     float *rows;     // [2] tiles: TC ring rows for warp 0
     float *line;     // [PROD][2] tiles: delayed inputs of each stage
     float *dx;       // [2] tiles: group delay line values for the last stage
-    uint64_t *bars;  // [PROD][2] mbarriers
+    uint64_t *bars;  // [PROD][2] mbarriers of the producers' fetches
+    uint64_t *full;  // [ring blocks] the last producer has written this block of the sample ring
+    uint64_t *empty; // [ring blocks] every active lane of the clock warp has moved past this block
 };
 
 // Global arrays are blocked by groups of 32 channels ([group][row][32]), so a block of 32 rows of one group is 4 KB of
@@ -412,6 +427,10 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
     s.dx = s.line + PROD * 2 * SB * kTile;
     s.bars = reinterpret_cast<uint64_t *>(s.dx + 2 * SB * kTile);
     constexpr int kStepRows = SB * kBlockRows;
+    constexpr int kStepShift = SB == 1 ? 5 : 6;       // log2(kStepRows)
+    const int ring_blocks = a.ring_slots >> kStepShift;  // step-sized block slots of the sample ring (a power of two >= 2)
+    s.full = s.bars + PROD * 2;
+    s.empty = s.full + ring_blocks;
     const int ring_mask = a.ring_slots - 1;
     for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) {
         s.taps[i] = a.mmse_taps[i];
@@ -428,6 +447,11 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
     const bool valid = ch < a.n_ch;
     if (threadIdx.x < PROD * 2) {
         mbar_init(s.bars + threadIdx.x, 1);
+    }
+    if ((int) threadIdx.x < 2 * ring_blocks) {
+        // full[] and empty[] are adjacent. Every lane of the signalling warp arrives for itself (count 32): each lane's own
+        // ring accesses are then ordered by its own arrival, which is also what compute-sanitizer's racecheck can follow.
+        mbar_init(s.full + threadIdx.x, 32);
     }
     if (threadIdx.x == 0) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -486,8 +510,9 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
 
     const uint32_t taps_base = smem_u32(s.taps);
     __syncthreads();
-    for (int t = 0; t < n_steps; t++) {
-        if (warp < PROD) {
+    if (warp < PROD) {
+        // ---- producers: PROD pipeline stages in lock step among themselves -------------------------------------------------
+        for (int t = 0; t < n_steps - 1; t++) {
             const int b = t - warp;
             if (b >= 0 && b < n_blocks) {
                 const int nr = min(kStepRows, a.n_rows - b * kStepRows);
@@ -513,6 +538,13 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                         bulk_commit();
                     }
                 }
+                if (warp == PROD - 1) {
+                    // this block's slot of the sample ring still holds block b - ring_blocks (for the first blocks: the samples
+                    // carried over from the previous call, or nothing): wait until the clock warp has let go of it. The wait is
+                    // over before it starts unless the clock has fallen a whole ring behind. (Probing the barrier at the top
+                    // of the step and waiting only after a failed probe was measured: slower, 1.80 -> 1.89 ms.)
+                    mbar_wait(s.empty + (b & (ring_blocks - 1)), (uint32_t) ((b / ring_blocks) & 1));
+                }
 #pragma unroll
                 for (int h = 0; h < SB; h++) {
                     const int nr_h = nr - h * kBlockRows;
@@ -525,25 +557,48 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                 if (has_dc && warp < PROD - 1) {
                     fence_async_smem();  // the next stage sends this tile to its delay line with a bulk store
                 }
+                if (warp == PROD - 1) {
+                    mbar_arrive(s.full + (b & (ring_blocks - 1)));  // every lane announces its rows of the block (release, CTA scope)
+                }
                 cur = nxt;
                 // this step's delay-line stores are done before the step ends: their source tile is recycled two steps
                 // later and the lines are read again at the earliest one step later
-                if (elect_one()) {  // always the same lane for the full mask: it owns the warp's bulk groups
+                if (has_dc && elect_one()) {  // always the same lane for the full mask: it owns the warp's bulk groups
                     bulk_wait_step(store_slack);
                 }
             }
-        } else {
-            // Mueller & Mueller loop over everything the last producer finished before this step
-            const int done_blocks = t - PROD + 1;
-            const int avail = history + (done_blocks <= 0 ? 0 : min(a.n_rows, done_blocks * kStepRows));
+            if (PROD > 1) {
+                producers_barrier(PROD * 32);
+            }
+        }
+    } else {
+        // ---- Mueller & Mueller loop: consumer of the sample ring -----------------------------------------------------------
+        int seen = 0;  // blocks known to be complete
+        // Blocks handed back to the producer so far. Rows before this call's row 0 count as blocks -1, -2, ...: they sit in the
+        // ring's last slots and hold the carried samples, so those slots are released like any other, once the lanes have moved
+        // past them; the slots in front of them are free from the start. (Block j >= -ring_blocks lives in slot j mod ring_blocks.)
+        int released = -ring_blocks;
+        {
+            const int first_held = __reduce_min_sync(0xffffffffu, (-history - 3) >> kStepShift);  // floor: block of the oldest row
+            for (int j = released; j < first_held; j++) {
+                mbar_arrive(s.empty + (j & (ring_blocks - 1)));
+            }
+            released = first_held;
+        }
+        while (true) {
+            if (seen < n_blocks) {
+                mbar_wait(s.full + (seen & (ring_blocks - 1)), (uint32_t) ((seen / ring_blocks) & 1));
+                seen++;
+            }
+            const int avail = history + min(a.n_rows, seen * kStepRows);
             // The body is branch-free: the reference's three data-dependent paths (leading zero taps, NaN output, loop
             // update) are computed side by side and selected, so that lanes in different situations stay converged and the
             // iteration is one dependent chain of ~40 operations instead of a sequence of divergent regions.
             // (A variant in which every lane makes the warp's trips with its stores and updates switched off was measured:
             // idle lanes must then be kept away from ring rows that are still being written, and the extra select on the
             // window address costs more than the uniform control flow saves.)
-            while (run_clock && ii >= 0 && ii + 7 < avail && oo < a.max_out) {
-                if (avail + kStepRows - (ii - 3) > a.ring_slots) {  // the lane fell behind its ring (pathological input)
+            while (run_clock && !overflow && ii >= 0 && ii + 7 < avail && oo < a.max_out) {
+                if (ii - 3 - history < released * kStepRows) {  // the lane went back into rows it had let go of (pathological input)
                     overflow = true;
                     break;
                 }
@@ -583,6 +638,7 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                     // fsk_demod.c:106, volk_32f_s32f_convert_8i: saturate(rint(x * 127)). The clamped value plus 1.5 * 2^23
                     // carries rint(x) in two's complement in its low mantissa bits (out is never NaN here).
                     const float scaled = fminf(fmaxf(__fmul_rn(out, 127.0f), -128.0f), 127.0f);
+                    // (packing four symbols into one 32-bit store was measured: slower, 1.80 -> 1.85 ms)
                     hard[oo] = (int8_t) (__float_as_int(__fadd_rn(scaled, 12582912.0f)) & 0xff);
                 }
                 const float mm_val = __fsub_rn(__fmul_rn(slice_pm1(last_sample), out), __fmul_rn(slice_pm1(out), last_sample));
@@ -597,8 +653,20 @@ __global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_
                 omega = nan ? omega : omega_next;
                 oo++;
             }
+            if (seen >= n_blocks) {
+                break;  // everything the producers will ever deliver has been looked at
+            }
+            // Blocks that no active lane will read again go back to the producer: the oldest row a lane still needs is the start
+            // of its window, ii - 3 (in rows of this call: minus the carried samples). Lanes that have stopped for good
+            // (padding, symbol capacity reached, error) do not hold anything.
+            const bool active = run_clock && !overflow && ii >= 0 && oo < a.max_out;
+            const int oldest_row = __reduce_min_sync(0xffffffffu, active ? ii - 3 - history : 0x7fffffff);
+            const int free_to = min(oldest_row >> kStepShift, seen);  // arithmetic shift: floor, also among the carried samples
+            for (int j = released; j < free_to; j++) {
+                mbar_arrive(s.empty + (j & (ring_blocks - 1)));  // every lane: its own reads of the block are behind it
+            }
+            released = max(released, free_to);
         }
-        __syncthreads();
     }
 
     if (warp < PROD) {
@@ -714,7 +782,7 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
     for (; sb >= 1; sb--) {
         const size_t tiles = (size_t) (prod - 1) * 2 + 2 + (size_t) prod * 2 + 2;
         const size_t floats = (size_t) kTapsFloats + (size_t) (args->ring_slots + kMirror) * 32 + tiles * sb * kTile;
-        smem = floats * sizeof(float) + (size_t) prod * 2 * sizeof(uint64_t);
+        smem = floats * sizeof(float) + ((size_t) prod * 2 + 2 * (size_t) (args->ring_slots / (sb * kBlockRows))) * sizeof(uint64_t);
         const int step_rows = sb * kBlockRows;
         const bool fits = smem <= (size_t) optin && args->ring_slots >= 2 * step_rows + kGuard + 16 &&
                           (!has_dc || (args->dc_length >= step_rows && args->dx_length >= 2 * args->dc_length - 2 + 8 * step_rows));
