@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <new>
 
 #include "sdrm_cuda.h"
 #include "device_math.cuh"
@@ -40,12 +41,13 @@ constexpr int kTile = kThreads * kR;      // outputs per CTA
 constexpr int kW1 = kR + 2;               // D=1: samples in the register window = taps per window period
 constexpr int kW2 = kR + 1;               // D=2: sample pairs in the register window; 2 * kW2 taps per window period
 constexpr int kTapBlock = FIR_TAPBLOCK;   // multiple of kW1 and 2 * kW2 (528 = 44 * 12 = 24 * 22 for 10 outputs per thread)
+static_assert(kTapBlock == SDRM_FIR_TAP_BLOCK, "sdrm_cuda.h names the tap block for the host layer");
 static_assert(kTapBlock % kW1 == 0 && kTapBlock % (2 * kW2) == 0 && kR % 2 == 0, "tap block must hold whole window periods");
 constexpr int kSlack = 32;                // float2 of read-ahead slack after each staged sample window
 constexpr int kMaxDevices = 64;           // per-device "function attributes are set" flags
 constexpr int kMaxGridY = 65535;          // kernels that put rows in gridDim.y loop over the rows beyond it
 
-struct FirParams {
+struct FirCommon {
     const float2 *in;
     size_t in_stride;
     const float2 *hist;
@@ -70,12 +72,26 @@ struct FirParams {
     int n_stages;
     float2 one;         // (1, 1)    runtime so that the compiler cannot simplify the exact-mode FFMA2 pair
     float2 negzero;     // (-0, -0)
-    // Filters of at most kTapBlock taps carry their (h, h) pairs in the kernel parameters: the taps are the same for every thread, so
-    // they can reach the FFMA2 through the constant bank and a uniform register instead of a shared-memory load per tap and warp.
-    // In FMA mode that is what lifts the pipe limit: FFMA2 acc = x * h + acc with three 64-bit register operands tops out at 74 % of
-    // the pipe (ncu: math pipe throttle at 74 % busy), with h in a uniform register it reads two.
-    float2 taps_c[kTapBlock];
+    // A long filter in FMA mode runs as several launches, each over the tap blocks [block_first, block_first + n_blocks_here) with
+    // that range's taps in its parameters; the accumulators travel between the launches through `acc` (float2 [row][tile][kTile]):
+    // read when block_first > 0, written unless this launch holds the filter's last block. The summation order does not change.
+    int block_first;
+    int n_blocks_here;
+    float2 *acc;
 };
+
+// Filters of at most CAP taps (per launch) carry their (h, h) pairs in the kernel parameters: the taps are the same for every thread,
+// so they can reach the FFMA2 through the constant bank and a uniform register instead of a shared-memory load per tap and warp.
+// In FMA mode that is what lifts the pipe limit: FFMA2 acc = x * h + acc with three 64-bit register operands tops out at 74 % of
+// the pipe (ncu: math pipe throttle at 74 % busy), with h in a uniform register it reads two.
+template <int CAP>
+struct FirParamsT : FirCommon {
+    float2 taps_c[CAP];
+};
+
+constexpr int kLongBlocks = 7;  // tap blocks per launch of a long FMA-mode filter: 7 x 528 (h, h) pairs = 29.6 KB of the 32 KB of parameters
+typedef FirParamsT<kTapBlock> FirParams;
+typedef FirParamsT<kLongBlocks * kTapBlock> FirParamsLong;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -131,13 +147,13 @@ __device__ __forceinline__ float2 lo(const float4 &v) { return make_float2(v.x, 
 __device__ __forceinline__ float2 hi(const float4 &v) { return make_float2(v.z, v.w); }
 
 // ---- decimation 1: acc[r] += s[j + r] * h[j]; register window of 12 samples, period 12 taps -------------------
-template <bool FAST, bool ALIGNED, bool GUARD, bool TP>
-__device__ __forceinline__ void fir_d1_body(float2 (&acc)[kR], float4 (&w)[kW1 / 2], const float2 *s, const float2 *hs, const FirParams &p,
+template <bool FAST, bool ALIGNED, bool GUARD, bool TP, typename P>
+__device__ __forceinline__ void fir_d1_body(float2 (&acc)[kR], float4 (&w)[kW1 / 2], const float2 *s, const float2 *hs, const P &p,
                                             int j, int ju, int n_taps, float2 one, float2 negzero) {
 #pragma unroll
     for (int u = 0; u < kW1; u++) {
         if (!GUARD || j + u < n_taps) {
-            float2 h = TP ? p.taps_c[(FAST ? ju : j) + u] : hs[j + u];
+            float2 h = TP ? p.taps_c[ju + u] : hs[j + u];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
                 const int e = (u + r) % kW1;
@@ -152,42 +168,46 @@ __device__ __forceinline__ void fir_d1_body(float2 (&acc)[kR], float4 (&w)[kW1 /
     }
 }
 
-template <bool FAST, bool ALIGNED, bool TP>
-__device__ __forceinline__ void fir_d1_block(float2 (&acc)[kR], const float2 *s, const float2 *hs, const FirParams &p, int n_taps,
-                                             float2 one, float2 negzero) {
+// tap_base: index in p.taps_c of this block's first tap (0 for a single-block filter)
+template <bool FAST, bool ALIGNED, bool TP, typename P>
+__device__ __forceinline__ void fir_d1_block(float2 (&acc)[kR], const float2 *s, const float2 *hs, const P &p, int n_taps,
+                                             int tap_base, float2 one, float2 negzero) {
     float4 w[kW1 / 2];
 #pragma unroll
     for (int k = 0; k < kW1 / 2; k++) {
         w[k] = ld_pair<ALIGNED>(s + 2 * k);
     }
     int j = 0;
-    // the same count, used only to index the parameter taps and hidden from the optimiser (which would merge it with j again),
-    // so that it can live in a uniform register and the taps be loaded into uniform registers
-    int ju;
-    asm volatile("mov.u32 %0, 0;" : "=r"(ju));
+    // In FMA mode the parameter taps are indexed with a count of their own, hidden from the optimiser (which would merge it with j
+    // again), so that it can live in a uniform register and the taps be loaded into uniform registers. Exact mode indexes them with
+    // the sample counter (see the launcher).
+    int ju = tap_base;
+    if (FAST) {
+        asm volatile("mov.u32 %0, %1;" : "=r"(ju) : "r"(tap_base));
+    }
     for (; j + kW1 <= n_taps; j += kW1, ju += kW1) {
-        fir_d1_body<FAST, ALIGNED, false, TP>(acc, w, s, hs, p, j, ju, n_taps, one, negzero);
+        fir_d1_body<FAST, ALIGNED, false, TP>(acc, w, s, hs, p, j, FAST ? ju : tap_base + j, n_taps, one, negzero);
     }
     if (j < n_taps) {
-        fir_d1_body<FAST, ALIGNED, true, TP>(acc, w, s, hs, p, j, ju, n_taps, one, negzero);
+        fir_d1_body<FAST, ALIGNED, true, TP>(acc, w, s, hs, p, j, FAST ? ju : tap_base + j, n_taps, one, negzero);
     }
 }
 
 // ---- decimation 2: acc[r] += s[j + 2r] * h[j]; even/odd windows of 11 samples each, period 22 taps ------------
-template <bool FAST, bool ALIGNED, bool GUARD, bool TP>
-__device__ __forceinline__ void fir_d2_body(float2 (&acc)[kR], float4 (&w)[kW2], const float2 *s, const float2 *hs, const FirParams &p,
+template <bool FAST, bool ALIGNED, bool GUARD, bool TP, typename P>
+__device__ __forceinline__ void fir_d2_body(float2 (&acc)[kR], float4 (&w)[kW2], const float2 *s, const float2 *hs, const P &p,
                                             int j, int ju, int n_taps, float2 one, float2 negzero) {
 #pragma unroll
     for (int q = 0; q < kW2; q++) {
         if (!GUARD || j + 2 * q < n_taps) {
-            float2 h = TP ? p.taps_c[(FAST ? ju : j) + 2 * q] : hs[j + 2 * q];
+            float2 h = TP ? p.taps_c[ju + 2 * q] : hs[j + 2 * q];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
                 acc[r] = mac2<FAST>(acc[r], lo(w[(q + r) % kW2]), h, one, negzero);
             }
         }
         if (!GUARD || j + 2 * q + 1 < n_taps) {
-            float2 h = TP ? p.taps_c[(FAST ? ju : j) + 2 * q + 1] : hs[j + 2 * q + 1];
+            float2 h = TP ? p.taps_c[ju + 2 * q + 1] : hs[j + 2 * q + 1];
 #pragma unroll
             for (int r = 0; r < kR; r++) {
                 acc[r] = mac2<FAST>(acc[r], hi(w[(q + r) % kW2]), h, one, negzero);
@@ -199,29 +219,31 @@ __device__ __forceinline__ void fir_d2_body(float2 (&acc)[kR], float4 (&w)[kW2],
     }
 }
 
-template <bool FAST, bool ALIGNED, bool TP>
-__device__ __forceinline__ void fir_d2_block(float2 (&acc)[kR], const float2 *s, const float2 *hs, const FirParams &p, int n_taps,
-                                             float2 one, float2 negzero) {
+template <bool FAST, bool ALIGNED, bool TP, typename P>
+__device__ __forceinline__ void fir_d2_block(float2 (&acc)[kR], const float2 *s, const float2 *hs, const P &p, int n_taps,
+                                             int tap_base, float2 one, float2 negzero) {
     float4 w[kW2];
 #pragma unroll
     for (int k = 0; k < kW2; k++) {
         w[k] = ld_pair<ALIGNED>(s + 2 * k);
     }
     int j = 0;
-    int ju;
-    asm volatile("mov.u32 %0, 0;" : "=r"(ju));
+    int ju = tap_base;
+    if (FAST) {
+        asm volatile("mov.u32 %0, %1;" : "=r"(ju) : "r"(tap_base));
+    }
     for (; j + 2 * kW2 <= n_taps; j += 2 * kW2, ju += 2 * kW2) {
-        fir_d2_body<FAST, ALIGNED, false, TP>(acc, w, s, hs, p, j, ju, n_taps, one, negzero);
+        fir_d2_body<FAST, ALIGNED, false, TP>(acc, w, s, hs, p, j, FAST ? ju : tap_base + j, n_taps, one, negzero);
     }
     if (j < n_taps) {
-        fir_d2_body<FAST, ALIGNED, true, TP>(acc, w, s, hs, p, j, ju, n_taps, one, negzero);
+        fir_d2_body<FAST, ALIGNED, true, TP>(acc, w, s, hs, p, j, FAST ? ju : tap_base + j, n_taps, one, negzero);
     }
 }
 
 // Issues the TMA copies for one tap block of one tile: samples v[start, start + count) and taps [j0, j0 + nt).
 // start is even; the window may straddle the history / input boundary and the end of the input.
 template <bool TP>
-__device__ void stage_load(const FirParams &p, int row, long long start, int count, int j0, int nt, float2 *smp, float2 *tps,
+__device__ void stage_load(const FirCommon &p, int row, long long start, int count, int j0, int nt, float2 *smp, float2 *tps,
                            uint64_t *bar) {
     const float2 *hist_row = p.hist + (size_t) row * p.hist_len;
     const float2 *in_row = p.in + (size_t) row * p.in_stride;
@@ -259,8 +281,8 @@ __device__ void stage_load(const FirParams &p, int row, long long start, int cou
     }
 }
 
-template <int D, bool FAST, bool ALIGNED, bool TP>
-__global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_tile_kernel(const FirParams p) {
+template <int D, bool FAST, bool ALIGNED, bool TP, typename P>
+__global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_tile_kernel(const P p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[2];
     __shared__ float2 last_out[kThreads];
@@ -279,22 +301,25 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_
     const int odd = (int) (v0 & 1);
     const long long v0_al = v0 - odd;
     const int window = (kTile - 1) * D + 1;  // samples spanned by the tile's outputs for one tap
-    const int n_blocks = (p.n_taps + kTapBlock - 1) / kTapBlock;
+    // tap blocks of this launch: all of them, except for a long FMA-mode filter that runs as several launches
+    const int n_blocks = p.n_blocks_here;
+    const int block_first = p.block_first;
+    const bool last_launch = (block_first + n_blocks) * kTapBlock >= p.n_taps;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (p.out_mode == SDRM_FIR_OUT_QD_PAIR) {
+    if (p.out_mode == SDRM_FIR_OUT_QD_PAIR && last_launch) {
         for (int i = tid; i < 257; i += kThreads) {
             atan_s[i] = p.atan_table[i];
         }
     }
     __syncthreads();
 
-    auto issue = [&](int b, int st) {
-        const int j0 = b * kTapBlock;
+    auto issue = [&](int b, int st) {  // b: tap block of this launch
+        const int j0 = (block_first + b) * kTapBlock;
         const int nt = min(kTapBlock, p.n_taps - j0);
         // taps [j0, j0 + nt) of this tile touch v0 + j0 ... v0 + j0 + window + nt - 2
         const int count = (odd + window + nt - 1 + 1) & ~1;
@@ -310,9 +335,20 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_
     }
 
     float2 acc[kR];
+    // accumulators in flight between the launches of a long filter: float2 [row][tile][kTile], a thread's kR values contiguous
+    float2 *const acc_mine = p.acc == nullptr ? nullptr : p.acc + (((size_t) row * gridDim.y + tile) * kThreads + tid) * kR;
+    if (block_first > 0) {
 #pragma unroll
-    for (int r = 0; r < kR; r++) {
-        acc[r] = make_float2(0.0f, 0.0f);
+        for (int r = 0; r < kR; r += 2) {
+            const float4 v = *reinterpret_cast<const float4 *>(acc_mine + r);
+            acc[r] = make_float2(v.x, v.y);
+            acc[r + 1] = make_float2(v.z, v.w);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            acc[r] = make_float2(0.0f, 0.0f);
+        }
     }
     const float2 one = p.one;
     const float2 negzero = p.negzero;
@@ -322,16 +358,16 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_
 
     for (int b = 0; b < n_blocks; b++) {
         const int st = (p.n_stages > 1) ? (b & 1) : 0;
-        const int nt = min(kTapBlock, p.n_taps - b * kTapBlock);
+        const int nt = min(kTapBlock, p.n_taps - (block_first + b) * kTapBlock);
         mbar_wait(&bars[st], (uint32_t) ((p.n_stages > 1 ? (b >> 1) : b) & 1));
         const float2 *smp = smem_f2 + st * stage_f2;
         const float2 *tps = smp + p.stage_samples;
         const float2 *s = smp + odd + tid * (kR * D);
         if (warp_has_outputs) {
             if (D == 1) {
-                fir_d1_block<FAST, ALIGNED, TP>(acc, s, tps, p, nt, one, negzero);
+                fir_d1_block<FAST, ALIGNED, TP>(acc, s, tps, p, nt, b * kTapBlock, one, negzero);
             } else {
-                fir_d2_block<FAST, ALIGNED, TP>(acc, s, tps, p, nt, one, negzero);
+                fir_d2_block<FAST, ALIGNED, TP>(acc, s, tps, p, nt, b * kTapBlock, one, negzero);
             }
         }
         if (b + p.n_stages < n_blocks) {
@@ -342,6 +378,13 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_
         }
     }
 
+    if (!last_launch) {
+#pragma unroll
+        for (int r = 0; r < kR; r += 2) {
+            *reinterpret_cast<float4 *>(acc_mine + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+        }
+        return;
+    }
     const long long m_first = m0 + (long long) tid * kR;
     if (p.out_mode == SDRM_FIR_OUT_ROWS) {
         float2 *out = reinterpret_cast<float2 *>(p.out) + (size_t) row * p.out_stride;
@@ -386,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, D == 1 ? FIR_CTAS1 : FIR_CTAS2) fir_
 // Any decimation: one thread per output, samples read through L1/L2. Only used where the FIR is a negligible share
 // of the chain (lpf2 behind a large decimation) or for unusual standalone filters.
 template <bool FAST>
-__global__ void fir_generic_kernel(const FirParams p) {
+__global__ void fir_generic_kernel(const FirCommon p) {
     const long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= p.n_out) {
         return;
@@ -422,7 +465,7 @@ __global__ void fir_generic_kernel(const FirParams p) {
 constexpr int kDecOutputs = 128;
 
 template <bool FAST>
-__global__ void __launch_bounds__(kDecOutputs) fir_dec_kernel(const FirParams p, int seg_len, int n_segs) {
+__global__ void __launch_bounds__(kDecOutputs) fir_dec_kernel(const FirCommon p, int seg_len, int n_segs) {
     extern __shared__ __align__(16) float2 dec_smem[];
     float2 *taps_s = dec_smem;                  // n_taps (h, h) pairs
     float2 *span = dec_smem + p.n_taps;         // n_segs segments of seg_len (>= D, odd) samples
@@ -506,9 +549,9 @@ __global__ void quad_demod_carry_kernel(const float2 *in, size_t in_stride, floa
     }
 }
 
-template <int D, bool FAST, bool ALIGNED, bool TP>
-int launch_tile_tp(const FirParams &p, int rows, int tiles, size_t smem, cudaStream_t stream) {
-    auto kernel = fir_tile_kernel<D, FAST, ALIGNED, TP>;
+template <int D, bool FAST, bool ALIGNED, bool TP, typename P>
+int launch_tile_tp(const P &p, int rows, int tiles, size_t smem, cudaStream_t stream) {
+    auto kernel = fir_tile_kernel<D, FAST, ALIGNED, TP, P>;
     cudaError_t err = cudaSuccess;
     // Function attributes are per device and sticky: set them once per (instantiation, device) for the largest size this
     // instantiation can ask for (two stages), not on every launch (~10 us each, most of a single-handle call's launch time).
@@ -537,12 +580,49 @@ int launch_tile_tp(const FirParams &p, int rows, int tiles, size_t smem, cudaStr
 template <int D, bool FAST, bool ALIGNED>
 int launch_tile(const FirParams &p, bool taps_in_params, int rows, int tiles, size_t smem, cudaStream_t stream) {
     if (taps_in_params) {
-        return launch_tile_tp<D, FAST, ALIGNED, true>(p, rows, tiles, smem, stream);
+        return launch_tile_tp<D, FAST, ALIGNED, true, FirParams>(p, rows, tiles, smem, stream);
     }
-    return launch_tile_tp<D, FAST, ALIGNED, false>(p, rows, tiles, smem, stream);
+    return launch_tile_tp<D, FAST, ALIGNED, false, FirParams>(p, rows, tiles, smem, stream);
+}
+
+// A long filter in FMA mode: ceil(n_blocks / kLongBlocks) launches, each with its tap blocks in the kernel parameters (uniform
+// loads, h as the FFMA2's uniform operand, as for short filters) and the accumulators carried through `acc` in between. The
+// parameter block is 30 KB, so it lives on the heap, one per calling thread.
+template <int D, bool ALIGNED>
+int launch_tile_long(const FirCommon &common, const float2 *h_taps_dup, int n_blocks, int rows, int tiles, size_t smem,
+                     cudaStream_t stream) {
+    static thread_local FirParamsLong *params = nullptr;
+    if (params == nullptr) {
+        params = new (std::nothrow) FirParamsLong;
+        if (params == nullptr) {
+            return -12;
+        }
+    }
+    static_cast<FirCommon &>(*params) = common;
+    for (int first = 0; first < n_blocks; first += kLongBlocks) {
+        const int here = n_blocks - first < kLongBlocks ? n_blocks - first : kLongBlocks;
+        const int tap0 = first * kTapBlock;
+        const int n_here = common.n_taps - tap0 < here * kTapBlock ? common.n_taps - tap0 : here * kTapBlock;
+        memcpy(params->taps_c, h_taps_dup + tap0, (size_t) n_here * sizeof(float2));
+        for (int j = n_here; j < kLongBlocks * kTapBlock; j++) {
+            params->taps_c[j] = make_float2(0.0f, 0.0f);
+        }
+        params->block_first = first;
+        params->n_blocks_here = here;
+        const int code = launch_tile_tp<D, true, ALIGNED, true, FirParamsLong>(*params, rows, tiles, smem, stream);
+        if (code != 0) {
+            return code;
+        }
+    }
+    return 0;
 }
 
 }  // namespace
+
+extern "C" size_t sdrm_cu_fir_scratch_bytes(int rows, int max_out) {
+    const size_t tiles = ((size_t) max_out + (kTile - 2) - 1) / (kTile - 2);  // the quad-demod tiling has the shorter stride
+    return (size_t) rows * tiles * kTile * sizeof(float2);
+}
 
 extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
     cudaStream_t stream = (cudaStream_t) stream_ptr;
@@ -575,6 +655,9 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
     p.atan_table = a->atan_table;
     p.one = make_float2(1.0f, 1.0f);
     p.negzero = make_float2(-0.0f, -0.0f);
+    p.block_first = 0;
+    p.n_blocks_here = 0;
+    p.acc = nullptr;
 
     if (a->decimation > 2) {
         if (qd) {
@@ -593,10 +676,10 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
             cudaError_t derr;
             if (a->fast) {
                 derr = cudaFuncSetAttribute(fir_dec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_smem);
-                fir_dec_kernel<true><<<dgrid, kDecOutputs, dec_smem, stream>>>(p, seg_len, n_segs);
+                fir_dec_kernel<true><<<dgrid, kDecOutputs, dec_smem, stream>>>(static_cast<const FirCommon &>(p), seg_len, n_segs);
             } else {
                 derr = cudaFuncSetAttribute(fir_dec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_smem);
-                fir_dec_kernel<false><<<dgrid, kDecOutputs, dec_smem, stream>>>(p, seg_len, n_segs);
+                fir_dec_kernel<false><<<dgrid, kDecOutputs, dec_smem, stream>>>(static_cast<const FirCommon &>(p), seg_len, n_segs);
             }
             if (derr != cudaSuccess) {
                 return -(int) derr - 1000;
@@ -606,9 +689,9 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
         }
         dim3 grid((unsigned) ((a->n_out + 127) / 128), (unsigned) (a->rows < kMaxGridY ? a->rows : kMaxGridY));
         if (a->fast) {
-            fir_generic_kernel<true><<<grid, 128, 0, stream>>>(p);
+            fir_generic_kernel<true><<<grid, 128, 0, stream>>>(static_cast<const FirCommon &>(p));
         } else {
-            fir_generic_kernel<false><<<grid, 128, 0, stream>>>(p);
+            fir_generic_kernel<false><<<grid, 128, 0, stream>>>(static_cast<const FirCommon &>(p));
         }
         cudaError_t err = cudaGetLastError();
         return err == cudaSuccess ? 0 : -(int) err - 1000;
@@ -634,6 +717,17 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
     // mode indexes them with the sample counter and gets a register-indexed constant load into ordinary registers: its FFMA2 pair
     // already takes -0 and 1 from uniform registers and an instruction has one uniform operand (h there: 7.65 ms), but the constant
     // load still saves the shared-memory load per tap and warp: K1 7.50 -> 7.45 ms, lpf2 0.966 -> 0.947 ms.
+    p.n_blocks_here = n_blocks;
+    if (a->fast && n_blocks > 1 && a->h_taps_dup != nullptr && a->acc_scratch != nullptr) {
+        // long filter, FMA mode: taps through the kernel parameters, kLongBlocks tap blocks per launch
+        p.acc = (float2 *) a->acc_scratch;
+        if (D == 1) {
+            return aligned ? launch_tile_long<1, true>(p, (const float2 *) a->h_taps_dup, n_blocks, a->rows, tiles, smem, stream)
+                           : launch_tile_long<1, false>(p, (const float2 *) a->h_taps_dup, n_blocks, a->rows, tiles, smem, stream);
+        }
+        return aligned ? launch_tile_long<2, true>(p, (const float2 *) a->h_taps_dup, n_blocks, a->rows, tiles, smem, stream)
+                       : launch_tile_long<2, false>(p, (const float2 *) a->h_taps_dup, n_blocks, a->rows, tiles, smem, stream);
+    }
     const bool taps_in_params = a->h_taps_dup != nullptr && n_blocks == 1;
     if (taps_in_params) {
         memcpy(p.taps_c, a->h_taps_dup, (size_t) a->n_taps * sizeof(float2));

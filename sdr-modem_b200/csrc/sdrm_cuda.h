@@ -55,7 +55,14 @@ typedef struct {
     float qd_gain;           /* QD_PAIR only */
     const float *atan_table; /* QD_PAIR only: 257 floats on the device */
     const void *h_taps_dup;  /* optional HOST copy of taps_dup (n_taps float2): short filters pass their taps as kernel parameters */
+    void *acc_scratch;       /* optional device scratch of sdrm_cu_fir_scratch_bytes(): with it a filter of more than one tap block
+                                runs in FMA mode as several launches with the taps in their parameters (decimation 1 or 2) */
 } sdrm_fir_args;
+
+#define SDRM_FIR_TAP_BLOCK 528 /* taps per block of the tile FIR (fir.cu kTapBlock) */
+
+/* bytes of sdrm_fir_args.acc_scratch for `rows` rows of at most max_out outputs per call (quad-demod mode included) */
+size_t sdrm_cu_fir_scratch_bytes(int rows, int max_out);
 
 int sdrm_cu_fir(const sdrm_fir_args *args, void *stream);
 

@@ -60,6 +60,7 @@ struct sdrm_fsk_demod_batch_t {
     int phase2;
     void *d_q; /* PAIR layout: quad demod output of the current call */
     size_t q_stride;
+    void *d_acc; /* FMA mode, filters of more than one tap block: accumulators between the launches of one filter (fir.cu) */
 
     /* TC ring */
     float *d_ring;
@@ -191,6 +192,11 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
     b->q_stride = sdrm_round_up(max_len, 2) + 2;
     code = sdrm_dev_zalloc(&b->d_q, (size_t) b->n_pairs * b->q_stride * 8);
     if (code != 0) goto fail;
+    if (b->fast && (b->t1 > SDRM_FIR_TAP_BLOCK || (b->t2 > SDRM_FIR_TAP_BLOCK && config->decimation <= 2))) {
+        /* the two filters run one after the other on one stream and share the scratch */
+        code = sdrm_dev_zalloc(&b->d_acc, sdrm_cu_fir_scratch_bytes((int) b->n_ch, (int) max_len));
+        if (code != 0) goto fail;
+    }
 
     /* clock + dc parameters (fsk_demod.c:53-66) */
     const float sps = (float) ((double) fs / config->baud_rate / config->decimation);
@@ -330,6 +336,7 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     f1.hist_len = b->hist1_len;
     f1.taps_dup = b->d_taps1;
     f1.h_taps_dup = b->h_taps1;
+    f1.acc_scratch = b->d_acc;
     f1.n_taps = b->t1;
     f1.decimation = 1;
     f1.phase = 0;
@@ -370,6 +377,7 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     f2.hist_len = b->hist2_len;
     f2.taps_dup = b->d_taps2;
     f2.h_taps_dup = b->h_taps2;
+    f2.acc_scratch = b->d_acc;
     f2.n_taps = b->t2;
     f2.decimation = dec;
     f2.phase = b->phase2;
@@ -721,6 +729,7 @@ void sdrm_fsk_demod_batch_destroy(sdrm_fsk_demod_batch *b) {
     cudaFree(b->d_atan);
     cudaFree(b->d_mmse);
     cudaFree(b->d_q);
+    cudaFree(b->d_acc);
     cudaFree(b->d_ring);
     cudaFree(b->d_delay);
     cudaFree(b->d_sums);

@@ -95,6 +95,25 @@ def test_fast_mode_counts_on_c2_64_channels(sdrm, ref):
     assert report["max_int8_delta"] <= 16
 
 
+@pytest.mark.parametrize("fs,baud,dec,chunk,n", [(480000, 9600, 2, 8192, 30000), (2400000, 2400, 100, 131072, 2 * 131072)],
+                         ids=["T1_1179_T2_577", "configs2_T1_9325"])
+def test_fast_mode_long_filters_equal_fma_order_reference(sdrm, ref, fs, baud, dec, chunk, n):
+    """Filters of more than one tap block (528 taps) run in FMA mode as several launches that carry their taps in the kernel
+    parameters and hand the accumulators on through a scratch buffer (fir.cu launch_tile_long): 3 + 2 tap blocks for the 480 ksps
+    shape, 18 blocks = 3 launches for the 9325-tap lpf1 of BASELINE configs[2]. Same summation order, so the result must still
+    be bit-identical to the FMA-order build of the reference."""
+    from oracle import ref as ref_module
+    if not ref_module.available(fma=True):
+        pytest.skip("oracle/_ref/libsdrmodem_ref_fma.so not built")
+    shape = workloads.DemodShape("long", fs, baud, 5000, dec, 2000, True, chunk)
+    iq = workloads.gfsk_channels(3, n, shape, seed=41).numpy()
+    got = run_fast(sdrm, shape.create_args, iq, chunk)
+    for c in range(3):
+        r = ref_module.fsk_chain(*shape.create_args, iq[c], chunk, fma=True)
+        assert len(r["hard"]) > 20
+        assert same_bits(got[c][0], r["hard"]) and same_bits(got[c][1], r["soft"]), "channel %d" % c
+
+
 # ---- the oracle, pinned again where the GPU tests run --------------------------------------------------------------------------
 @pytest.mark.parametrize("name", sorted(FSK_GOLDENS))
 def test_oracle_port_equals_reference_build_on_this_box(port, ref, name):
