@@ -178,8 +178,8 @@ def cpu_reference_run(shape, seconds, n_threads=None, build=False):
                "SIMD VOLK, not bit-identical)" % (ref.tuned_level(), ref.tuned_level())) if build == "tuned" else \
         "oracle/_ref strict build (-O2 -ffp-contract=off, VOLK generic shim)"
     return {"value": samples / sec / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": "%d channels (one per thread) x %d samples x %d passes, chunk %d, %.1f s, %s; compared per sample, so the "
-                      "channel count of the sample does not enter the ratio" % (cores, n, passes, shape.chunk, sec, flavour),
+            "sample": "%d ch (1/thread) x %d samples x %d passes, chunk %d, %.1f s; per-sample rate, channel count does not enter; %s"
+                      % (cores, n, passes, shape.chunk, sec, flavour),
             "seconds": sec, "symbols": int(symbols)}
 
 
@@ -237,10 +237,9 @@ def run_reference_arm(args, shape):
         results["tuned" if build else "strict"] = (total_samples / total_sec / 1e6, total_sec, passes)
     best = max(results, key=lambda k: results[k][0])
     value, total_sec, passes = results[best]
-    sample = ("%d channels (one per thread) x %d samples x %d passes per step, chunk %d; value = the faster of the CPU builds "
-              "(%s); strict = oracle/_ref -O2 -ffp-contract=off VOLK generic shim (parity-defining), tuned = -O3 "
-              "x86-64-v%d lane-partial SIMD dot products (SIMD VOLK stand-in); per-sample rate, the sample's channel count does "
-              "not enter" % (cores, n, passes, shape.chunk, best, ref.tuned_level()))
+    sample = ("faster of 2 CPU builds = %s; %d ch (1/thread) x %d samples x %d passes/step, chunk %d; per-sample rate, channel count "
+              "does not enter; strict = oracle/_ref -O2 -ffp-contract=off VOLK generic shim (parity-defining), tuned = -O3 "
+              "x86-64-v%d lane-partial SIMD dot products (SIMD VOLK stand-in)" % (best, cores, n, passes, shape.chunk, ref.tuned_level()))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_sec / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",

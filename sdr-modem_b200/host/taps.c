@@ -27,6 +27,11 @@ int sdrm_dev_zalloc(void **p, size_t bytes) {
     }
     SDRM_CUDA_TRY(cudaMalloc(p, bytes));
     SDRM_CUDA_TRY(cudaMemset(*p, 0, bytes));
+    /* cudaMemset of device memory is asynchronous and runs on the legacy default stream, which the library's non-blocking
+     * streams do not wait for: a buffer allocated lazily (the staging buffers of the first host-buffer call) could be zeroed
+     * AFTER the first copy into it had landed. Seen as one wrong symbol count on the first call of a shard when a second
+     * device's context was being brought up at the same time; the fill is finished before the pointer is handed out. */
+    SDRM_CUDA_TRY(cudaStreamSynchronize(0));
     return 0;
 }
 
