@@ -53,6 +53,9 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=10.0)
     p.add_argument("--debug-no-tail", action="store_true", help="measurement aid: skip the serial tail (invalid result)")
     p.add_argument("--full-line", default=None, help="also write the JSON line to this file")
+    p.add_argument("--single-process", action="store_true",
+                   help="one process drives --gpus N devices through the C multi-device entry points (sdrm_fsk_demod_multi_*): "
+                        "host buffers in, int8 out; not the driver's launch, which is one rank per GPU")
     return p.parse_args()
 
 
@@ -412,6 +415,65 @@ def run_c5(args, world, rank, local_rank, device, shape, fp32_peak, dist):
             "roofline_frac": value / world * 1e6 * flops / 1e12 / fp32_peak, "error_flags": flags}
 
 
+def run_single_process(args, shape):
+    """One process, N GPUs, through include/sdrm/sdrm_multi.h: the job's channels are split over the device list by channel range,
+    every device has its own host thread, stream set and pinned ring inside the library. The interface is host buffers, so the
+    figure is end to end by construction (pinned input, H2D, chain, D2H of the int8 symbols)."""
+    import torch
+    import sdrm
+    import workloads
+    n_dev = args.gpus
+    assert torch.cuda.device_count() >= n_dev, "needs %d visible GPUs" % n_dev
+    n_ch, chunk = args.channels * n_dev, args.chunk
+    cap = int(chunk / 20 * 1.1) + 64
+    multi = sdrm.FskDemodMulti(list(range(n_dev)), n_ch, *shape.create_args, chunk, max_symbols_per_call=cap)
+    pin_in = [sdrm.PinnedArray((n_ch, chunk), np.complex64) for _ in range(2)]
+    for g in range(n_dev):
+        dev = torch.device("cuda", g)
+        x = workloads.gfsk_channels(args.channels, 2 * chunk, shape, seed=1000 + g * args.channels, device=dev)
+        for i in range(2):
+            torch.from_numpy(pin_in[i].array[g * args.channels:(g + 1) * args.channels].view(np.float32)).copy_(
+                torch.view_as_real(x[:, i * chunk:(i + 1) * chunk].contiguous()).reshape(args.channels, 2 * chunk))
+        del x
+    for g in range(n_dev):
+        torch.cuda.synchronize(g)
+    pin_out = sdrm.PinnedArray((n_ch, cap), np.int8)
+    pin_len = sdrm.PinnedArray((n_ch,), np.uint32)
+
+    def loop(n):
+        fetched = 0
+        for k in range(n):
+            multi.submit_ptr(pin_in[k % 2].ptr, chunk, chunk)
+            if k + 1 >= 3:
+                multi.fetch_ptr(pin_out.ptr, cap, pin_len.ptr)
+                fetched += 1
+        while fetched < n:
+            multi.fetch_ptr(pin_out.ptr, cap, pin_len.ptr)
+            fetched += 1
+
+    steps = max(3, min(args.steps, 12))
+    loop(max(3, args.warmup))
+    multi.sync()
+    launches_before = multi.launch_count
+    t0 = time.perf_counter()
+    loop(steps)
+    multi.sync()
+    sec = time.perf_counter() - t0
+    launches = int(multi.launch_count - launches_before)
+    value = n_ch * chunk * steps / sec / 1e6
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_dev, "steps": steps, "warmup": max(3, args.warmup),
+            "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(c2_config(args, shape, "exact"), launch="one process, sdrm_fsk_demod_multi_* over %d "
+                                                "devices, one library thread per GPU" % n_dev),
+            "gpu_launches": launches,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": n_ch * chunk * 8, "d2h_bytes_per_step": n_ch * cap + n_ch * 4,
+                    "symbols_last_step": int(pin_len.array.sum())},
+            "note": "value IS the end-to-end figure here: the multi-device entry points take host buffers",
+            "shards": multi.shards(), "error_flags": multi.error_flags(), "lib": sdrm.version()}
+    multi.close()
+    emit_line(line, args.full_line)
+
+
 def main():
     args = parse_args()
     claim_stdout()
@@ -419,6 +481,9 @@ def main():
     shape = c2_shape(args.chunk)
     if args.impl == "reference":
         run_reference_arm(args, shape)
+        return
+    if args.single_process:
+        run_single_process(args, shape)
         return
 
     import torch
