@@ -41,6 +41,9 @@ def test_headers_exist():
 @pytest.mark.parametrize("header", HEADERS, ids=[os.path.basename(h) for h in HEADERS])
 def test_library_exports_every_declared_symbol(sdrm, header):
     names = declared_functions(header)
+    if os.path.basename(header) in ("server_config.h",):
+        assert not names  # a struct layout only (the reference's src/server_config.h:17-44), nothing to export
+        return
     assert names, "no declarations parsed from %s" % header
     for name in names:
         assert hasattr(sdrm.lib, name), "%s declared in %s but not exported" % (name, os.path.basename(header))
