@@ -269,6 +269,13 @@ int sdrm_measure_fp32_peak(int device, double *fma_tflops, double *exact_pair_tf
  */
 int sdrm_probe_h2d(int device, const void *host, void *d_scratch, size_t bytes, int repeats, double *seconds);
 
+/*
+ * Creates the CUDA context of `device` (-1 = current) and loads the library's kernels now instead of inside the first *_create
+ * (about two seconds on a B200 box). A server calls it while it starts up; SDRM_WARM_START=<device> in the environment makes the
+ * library do it when it is loaded. 0, or -EIO without a usable device.
+ */
+int sdrm_warm_start(int device);
+
 /* Library/runtime identification: "sdr-modem_b200 <version>; sm_100a; CUDA runtime <n>". */
 const char *sdrm_version(void);
 

@@ -5,6 +5,8 @@
  * (the 4- and 8-GPU end-to-end collapse had to be separated into platform limit and library overhead).
  * No kernel runs here and nothing of the reference corresponds to it.
  */
+#include <stdlib.h>
+
 #include "../../include/sdrm/sdrm_batch.h"
 #include "sdrm_internal.h"
 
@@ -36,4 +38,28 @@ int sdrm_probe_h2d(int device, const void *host, void *d_scratch, size_t bytes, 
     if (e1 != NULL) cudaEventDestroy(e1);
     if (stream != NULL) cudaStreamDestroy(stream);
     return code;
+}
+
+/*
+ * Warm start. Creating the CUDA context and loading this library's kernels takes about two seconds on a B200 box, and with lazy
+ * initialisation the first *_create of the process pays for it: the first client of a server then waits that long for its
+ * response (the reference's own integration test gives a client two seconds, test/test_tcp_server.c:406). A server calls
+ * sdrm_warm_start(device) while it starts up, or sets SDRM_WARM_START=<device> in its environment, in which case the library does
+ * it when it is loaded. Off by default: a process per GPU (torchrun) must not all touch device 0.
+ */
+int sdrm_warm_start(int device) {
+    if (device >= 0) {
+        SDRM_CUDA_TRY(cudaSetDevice(device));
+    }
+    SDRM_CUDA_TRY(cudaFree(NULL));
+    double fma = 0.0;
+    double pair = 0.0;
+    return sdrm_measure_fp32_peak(device, &fma, &pair); /* a first kernel launch: loads the module */
+}
+
+__attribute__((constructor)) static void sdrm_warm_start_from_environment(void) {
+    const char *text = getenv("SDRM_WARM_START");
+    if (text != NULL && text[0] != '\0') {
+        (void) sdrm_warm_start(atoi(text));
+    }
 }
