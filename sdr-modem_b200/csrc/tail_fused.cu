@@ -45,6 +45,14 @@
 
 namespace {
 
+// Register budget of the tail kernel. ptxas takes 168 registers when only the block size bounds it; capped at 144 it spills 8
+// bytes and the kernel is 4 % faster (1.835 -> 1.764 ms at C2; 152: 2.05 ms, 136: 2.17 ms: the schedule changes with the
+// allocation, measured, not predicted). What it does NOT change is what the tail costs the filter kernel beside it (K1 7.52 ms
+// against 7.30 alone at every budget): that cost is not a matter of how many K1 CTAs fit next to a tail CTA.
+#ifndef TAIL_REGS
+#define TAIL_REGS 144
+#endif
+#define TAIL_BOUNDS(threads) __maxnreg__(TAIL_REGS)
 constexpr int kBlockRows = 32;             // rows per pipeline step
 constexpr int kTile = kBlockRows * 32;     // floats per [row][lane] tile (4 KB)
 constexpr int kRowBytes = 32 * 4;          // one row of 32 channels
@@ -416,7 +424,7 @@ __device__ __forceinline__ void producer_block(const sdrm_tail_args &a, const La
 // at different symbol phases when more rows arrive at once, so two blocks per step are used wherever shared memory and the
 // delay-line lengths allow it (8 KB tiles).
 template <int PROD, int DIVSTEPS, bool FAST, int SB>
-__global__ void __launch_bounds__((PROD + 1) * 32) demod_tail_kernel(const sdrm_tail_args a) {
+__global__ void TAIL_BOUNDS((PROD + 1) * 32) demod_tail_kernel(const sdrm_tail_args a) {
     extern __shared__ __align__(128) float smem[];
     Layout s;
     s.taps = smem;
