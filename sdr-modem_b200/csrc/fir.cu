@@ -585,10 +585,10 @@ int launch_tile(const FirParams &p, bool taps_in_params, int rows, int tiles, si
     return launch_tile_tp<D, FAST, ALIGNED, false, FirParams>(p, rows, tiles, smem, stream);
 }
 
-// A long filter in FMA mode: ceil(n_blocks / kLongBlocks) launches, each with its tap blocks in the kernel parameters (uniform
+// A long filter: ceil(n_blocks / kLongBlocks) launches, each with its tap blocks in the kernel parameters (in FMA mode: uniform
 // loads, h as the FFMA2's uniform operand, as for short filters) and the accumulators carried through `acc` in between. The
 // parameter block is 30 KB, so it lives on the heap, one per calling thread.
-template <int D, bool ALIGNED>
+template <int D, bool FAST, bool ALIGNED>
 int launch_tile_long(const FirCommon &common, const float2 *h_taps_dup, int n_blocks, int rows, int tiles, size_t smem,
                      cudaStream_t stream) {
     static thread_local FirParamsLong *params = nullptr;
@@ -609,7 +609,7 @@ int launch_tile_long(const FirCommon &common, const float2 *h_taps_dup, int n_bl
         }
         params->block_first = first;
         params->n_blocks_here = here;
-        const int code = launch_tile_tp<D, true, ALIGNED, true, FirParamsLong>(*params, rows, tiles, smem, stream);
+        const int code = launch_tile_tp<D, FAST, ALIGNED, true, FirParamsLong>(*params, rows, tiles, smem, stream);
         if (code != 0) {
             return code;
         }
@@ -718,15 +718,27 @@ extern "C" int sdrm_cu_fir(const sdrm_fir_args *a, void *stream_ptr) {
     // already takes -0 and 1 from uniform registers and an instruction has one uniform operand (h there: 7.65 ms), but the constant
     // load still saves the shared-memory load per tap and warp: K1 7.50 -> 7.45 ms, lpf2 0.966 -> 0.947 ms.
     p.n_blocks_here = n_blocks;
-    if (a->fast && n_blocks > 1 && a->h_taps_dup != nullptr && a->acc_scratch != nullptr) {
-        // long filter, FMA mode: taps through the kernel parameters, kLongBlocks tap blocks per launch
+    if (n_blocks > 1 && a->h_taps_dup != nullptr && a->acc_scratch != nullptr) {
+        // long filter: taps through the kernel parameters, kLongBlocks tap blocks per launch (FMA mode: uniform registers, 71 -> 93 %
+        // of the pipe; exact mode: constant loads instead of a shared-memory load per tap and warp, worth 3 % as for short filters)
         p.acc = (float2 *) a->acc_scratch;
+        const float2 *taps = (const float2 *) a->h_taps_dup;
+#define SDRM_LONG(DD, FF, AA) return launch_tile_long<DD, FF, AA>(p, taps, n_blocks, a->rows, tiles, smem, stream)
         if (D == 1) {
-            return aligned ? launch_tile_long<1, true>(p, (const float2 *) a->h_taps_dup, n_blocks, a->rows, tiles, smem, stream)
-                           : launch_tile_long<1, false>(p, (const float2 *) a->h_taps_dup, n_blocks, a->rows, tiles, smem, stream);
+            if (a->fast) {
+                if (aligned) SDRM_LONG(1, true, true);
+                SDRM_LONG(1, true, false);
+            }
+            if (aligned) SDRM_LONG(1, false, true);
+            SDRM_LONG(1, false, false);
         }
-        return aligned ? launch_tile_long<2, true>(p, (const float2 *) a->h_taps_dup, n_blocks, a->rows, tiles, smem, stream)
-                       : launch_tile_long<2, false>(p, (const float2 *) a->h_taps_dup, n_blocks, a->rows, tiles, smem, stream);
+        if (a->fast) {
+            if (aligned) SDRM_LONG(2, true, true);
+            SDRM_LONG(2, true, false);
+        }
+        if (aligned) SDRM_LONG(2, false, true);
+        SDRM_LONG(2, false, false);
+#undef SDRM_LONG
     }
     const bool taps_in_params = a->h_taps_dup != nullptr && n_blocks == 1;
     if (taps_in_params) {

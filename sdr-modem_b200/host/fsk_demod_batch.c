@@ -60,7 +60,7 @@ struct sdrm_fsk_demod_batch_t {
     int phase2;
     void *d_q; /* PAIR layout: quad demod output of the current call */
     size_t q_stride;
-    void *d_acc; /* FMA mode, filters of more than one tap block: accumulators between the launches of one filter (fir.cu) */
+    void *d_acc; /* filters of more than one tap block: accumulators between the launches of one filter (fir.cu) */
 
     /* TC ring */
     float *d_ring;
@@ -192,7 +192,7 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
     b->q_stride = sdrm_round_up(max_len, 2) + 2;
     code = sdrm_dev_zalloc(&b->d_q, (size_t) b->n_pairs * b->q_stride * 8);
     if (code != 0) goto fail;
-    if (b->fast && (b->t1 > SDRM_FIR_TAP_BLOCK || (b->t2 > SDRM_FIR_TAP_BLOCK && config->decimation <= 2))) {
+    if (b->t1 > SDRM_FIR_TAP_BLOCK || (b->t2 > SDRM_FIR_TAP_BLOCK && config->decimation <= 2)) {
         /* the two filters run one after the other on one stream and share the scratch */
         code = sdrm_dev_zalloc(&b->d_acc, sdrm_cu_fir_scratch_bytes((int) b->n_ch, (int) max_len));
         if (code != 0) goto fail;
