@@ -12,10 +12,12 @@
 // Fast mode uses a single FFMA2 per tap (same order, fused rounding).
 //
 // Structure: one CTA = one row x TILE outputs; each thread owns R consecutive outputs and slides a register
-// window over the samples (one 16-byte LDS per two taps), taps are broadcast from shared memory as duplicated
-// (h, h) pairs. Samples (tile + halo) and taps are staged by 1-D TMA bulk copies (cp.async.bulk + mbarrier),
-// tap-blocked so that shared memory does not grow with the filter length, double-buffered when there is more
-// than one tap block.
+// window over the samples (one 16-byte LDS per two taps). The taps, duplicated (h, h) pairs, normally arrive in the
+// kernel parameters (constant bank: uniform registers in FMA mode, constant loads in exact mode), 528 per launch for a
+// short filter and 7 x 528 per launch for a long one, which then runs as several launches with its accumulators carried
+// through a scratch buffer; callers without a host copy of the taps or without scratch get them broadcast from shared
+// memory. Samples (tile + halo) are staged by 1-D TMA bulk copies (cp.async.bulk + mbarrier), tap-blocked so that
+// shared memory does not grow with the filter length, double-buffered when there is more than one tap block.
 
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1,3 +1,7 @@
+#!/usr/bin/env python3
+"""Measurement aid (GPU box, best with two or more GPUs): the multi-device entry points against the oracle in a loop, first with
+shards on one device, then across all devices, in one process. This sequence exposed the asynchronous cudaMemset race that
+sdrm_dev_zalloc now closes (a shard's first call after a second device's context came up).  usage: tools/stress_multi.py [iterations]"""
 import sys, os
 ROOT="/root/repo"
 sys.path.insert(0, ROOT); sys.path.insert(0, ROOT+"/sdr-modem_b200")
