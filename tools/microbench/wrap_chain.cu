@@ -144,6 +144,41 @@ __global__ void chain(const float *d_in, float *out, long long *cycles) {
     }
 }
 
+// onepred over a quad layout: [step / 4][lane][4], so that one LDS.128 / STS.128 moves four steps of a lane. One warp pays
+// about 5 cycles of issue per LDS.32 and 3 per STS.32 (lsu_issue.cu); measured on B200 this is NOT faster (23.75 cycles per step
+// against 20.52): the wrap chain itself (add, add, sign merge, select) is the 20 cycles, the memory instructions fit its stalls.
+__global__ void chain_quad(const float *d_in, float *out, long long *cycles) {
+    __shared__ __align__(16) float d[N * 32];
+    for (int i = threadIdx.x; i < N * 32; i += 32) {
+        const int step = i / 32, lane = i % 32;
+        d[((step >> 2) * 32 + lane) * 4 + (step & 3)] = d_in[i];
+    }
+    __syncwarp();
+    float p = 0.0f;
+    long long t0 = clock64();
+    float4 *col = reinterpret_cast<float4 *>(d) + threadIdx.x;
+    for (int pass = 0; pass < PASSES; pass++) {
+        for (int i0 = 0; i0 < N / 4; i0 += 8) {
+            float4 *c = col + i0 * 32;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float4 x = c[i * 32];
+                x.x = p = step_onepred(p, x.x);
+                x.y = p = step_onepred(p, x.y);
+                x.z = p = step_onepred(p, x.z);
+                x.w = p = step_onepred(p, x.w);
+                c[i * 32] = x;
+            }
+        }
+    }
+    long long t1 = clock64();
+    const int half = N / 2;
+    out[threadIdx.x] = p + d[((half >> 2) * 32 + threadIdx.x) * 4 + (half & 3)];
+    if (threadIdx.x == 0) {
+        *cycles = t1 - t0;
+    }
+}
+
 int main() {
     float *h = new float[N * 32];
     uint32_t r = 12345;
@@ -203,6 +238,20 @@ int main() {
     int same8 = 1;
     for (int i = 0; i < 32; i++) {
         same8 &= res[0][i] == res[8][i];
+    }
+    {
+        long long cq = 0;
+        float rq[32];
+        for (int rep = 0; rep < 2; rep++) {
+            chain_quad<<<1, 32>>>(d_in, out, cyc);
+            cudaMemcpy(&cq, cyc, 8, cudaMemcpyDeviceToHost);
+            cudaMemcpy(rq, out, 128, cudaMemcpyDeviceToHost);
+        }
+        int sameq = 1;
+        for (int i = 0; i < 32; i++) {
+            sameq &= rq[i] == res[3][i];
+        }
+        printf("onepred, quad layout (LDS.128 / STS.128 per 4 steps) %.2f (same=%d) cycles/step\n", cq / (double) (N * PASSES), sameq);
     }
     printf("viaddmin %.2f (same=%d) cycles/step\n", c[8] / (double) (N * PASSES), same8);
     printf("predadd %.2f (same=%d)  predadd_ptx %.2f (same=%d) cycles/step\n", c[6] / (double) (N * PASSES), same6,
