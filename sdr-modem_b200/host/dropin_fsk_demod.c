@@ -14,7 +14,12 @@ struct fsk_demod_t {
     int8_t *output; /* owned by the handle, valid until the next call (fsk_demod.c:24,108) */
     uint32_t output_len;
     uint32_t max_input_buffer_length;
+    int output_pinned;
 };
+
+/* results of up to this many symbols land in page-locked memory (a DMA straight from the device); larger handles keep a
+ * pageable buffer, which the driver stages */
+#define PINNED_OUTPUT_LIMIT ((size_t) 16 << 20)
 
 int fsk_demod_create(uint64_t sampling_freq, uint32_t baud_rate, int64_t deviation, uint8_t decimation,
                      uint32_t transition_width, bool use_dc_block, uint32_t max_input_buffer_length, fsk_demod **demod) {
@@ -39,7 +44,14 @@ int fsk_demod_create(uint64_t sampling_freq, uint32_t baud_rate, int64_t deviati
     }
     result->max_input_buffer_length = max_input_buffer_length;
     result->output_len = max_input_buffer_length;
-    result->output = malloc(sizeof(int8_t) * (result->output_len == 0 ? 1 : result->output_len));
+    const size_t output_bytes = sizeof(int8_t) * (result->output_len == 0 ? 1 : result->output_len);
+    if (output_bytes <= PINNED_OUTPUT_LIMIT) {
+        result->output = sdrm_pinned_alloc(output_bytes);
+        result->output_pinned = result->output != NULL;
+    }
+    if (result->output == NULL) {
+        result->output = malloc(output_bytes);
+    }
     if (result->output == NULL) {
         fsk_demod_destroy(result);
         return -ENOMEM;
@@ -66,6 +78,10 @@ void fsk_demod_destroy(fsk_demod *demod) {
         return;
     }
     sdrm_fsk_demod_batch_destroy(demod->batch);
-    free(demod->output);
+    if (demod->output_pinned) {
+        sdrm_pinned_free(demod->output);
+    } else {
+        free(demod->output);
+    }
     free(demod);
 }

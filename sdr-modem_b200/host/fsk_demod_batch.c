@@ -98,6 +98,8 @@ struct sdrm_fsk_demod_batch_t {
     float *d_soft[SLOTS];
     uint32_t *d_out_len[SLOTS];
     size_t out_stride;
+    size_t slot_bound[SLOTS]; /* most symbols the clock loop can produce from the rows of the call in this slot */
+    uint32_t *h_counts;       /* pinned, one per channel: the symbol counts of the call being fetched */
     cudaEvent_t ev_fir[SLOTS];
     cudaEvent_t ev_tail[SLOTS];
     cudaEvent_t ev_copy[SLOTS];
@@ -264,6 +266,8 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
     code = sdrm_dev_zalloc((void **) &b->d_carry, (size_t) b->ring_slots * b->n_ch_pad * sizeof(float));
     if (code != 0) goto fail;
     code = sdrm_dev_zalloc((void **) &b->d_error, sizeof(int));
+    if (code != 0) goto fail;
+    code = sdrm_cuda_code(cudaHostAlloc((void **) &b->h_counts, (size_t) b->n_ch_pad * sizeof(uint32_t), cudaHostAllocPortable), "pinned counts");
     if (code != 0) goto fail;
 
     b->out_stride = config->max_symbols_per_call != 0 ? config->max_symbols_per_call : max_len;
@@ -459,6 +463,10 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
         SDRM_CUDA_TRY(cudaEventRecord(b->ev_time[slot][5], b->s_tail));
     }
     b->last_slot = slot;
+    /* k symbols move the loop's cursor by sum floor(mu + omega) >= k * (omega_mid - omega_lim) - 1 rows
+     * (clock_recovery_mm.c:101-125), and it has this call's rows plus what it carried (less than 8 + 2 omega) to move over:
+     * the fetch copies this many columns and looks at the counts before it trusts the bound */
+    b->slot_bound[slot] = (size_t) (((double) n_rows + 16.0 + 2.0 * (b->omega_mid + b->omega_lim)) / (b->omega_mid - b->omega_lim)) + 4;
     SDRM_CUDA_TRY(cudaEventRecord(b->ev_tail[slot], b->s_tail));
     b->head += n_rows;
     b->submitted++;
@@ -574,6 +582,21 @@ int sdrm_fsk_demod_batch_submit_i16(sdrm_fsk_demod_batch *b, const int16_t *inpu
     return enqueue(b, b->d_in[slot], b->in_stride_dev, input_len, slot, 1);
 }
 
+static int copy_columns(sdrm_fsk_demod_batch *b, int slot, int8_t *output, float *soft, size_t out_stride, size_t first, size_t width) {
+    if (width == 0) {
+        return 0;
+    }
+    if (output != NULL) {
+        SDRM_CUDA_TRY(cudaMemcpy2DAsync(output + first, out_stride, b->d_hard[slot] + first, b->out_stride, width, b->n_ch,
+                                        cudaMemcpyDeviceToHost, b->s_out));
+    }
+    if (soft != NULL) {
+        SDRM_CUDA_TRY(cudaMemcpy2DAsync(soft + first, out_stride * sizeof(float), b->d_soft[slot] + first, b->out_stride * sizeof(float),
+                                        width * sizeof(float), b->n_ch, cudaMemcpyDeviceToHost, b->s_out));
+    }
+    return 0;
+}
+
 int sdrm_fsk_demod_batch_fetch(sdrm_fsk_demod_batch *b, int8_t *output, float *soft, size_t out_stride, uint32_t *output_len) {
     if (b == NULL || b->fetched >= b->submitted || (soft != NULL && !b->want_soft)) {
         return -1; /* nothing is enqueued and the call stays un-fetched */
@@ -582,22 +605,30 @@ int sdrm_fsk_demod_batch_fetch(sdrm_fsk_demod_batch *b, int8_t *output, float *s
     if (code != 0) return code;
     const int slot = (int) (b->fetched % SLOTS);
     const size_t width = out_stride < b->out_stride ? out_stride : b->out_stride;
+    /* Only the columns the call can have filled travel: a handle created for 2016000-sample buffers (the reference's perf
+     * program) and fed 4096 samples would otherwise move 2 MB for 400 symbols. */
+    const size_t first_pass = b->slot_bound[slot] < width ? b->slot_bound[slot] : width;
     /* results leave on their own stream so that a younger call's tail does not delay them */
     SDRM_CUDA_TRY(cudaStreamWaitEvent(b->s_out, b->ev_tail[slot], 0));
-    if (output != NULL) {
-        SDRM_CUDA_TRY(cudaMemcpy2DAsync(output, out_stride, b->d_hard[slot], b->out_stride, width, b->n_ch, cudaMemcpyDeviceToHost,
-                                        b->s_out));
-    }
-    if (soft != NULL) {
-        SDRM_CUDA_TRY(cudaMemcpy2DAsync(soft, out_stride * sizeof(float), b->d_soft[slot], b->out_stride * sizeof(float),
-                                        width * sizeof(float), b->n_ch, cudaMemcpyDeviceToHost, b->s_out));
-    }
-    if (output_len != NULL) {
-        SDRM_CUDA_TRY(cudaMemcpyAsync(output_len, b->d_out_len[slot], (size_t) b->n_ch * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                      b->s_out));
-    }
+    code = copy_columns(b, slot, output, soft, out_stride, 0, first_pass);
+    if (code != 0) return code;
+    SDRM_CUDA_TRY(cudaMemcpyAsync(b->h_counts, b->d_out_len[slot], (size_t) b->n_ch * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->s_out));
     SDRM_CUDA_TRY(cudaEventRecord(b->ev_done[slot], b->s_out));
     SDRM_CUDA_TRY(cudaEventSynchronize(b->ev_done[slot]));
+    uint32_t most = 0;
+    for (uint32_t c = 0; c < b->n_ch; c++) {
+        most = b->h_counts[c] > most ? b->h_counts[c] : most;
+    }
+    if ((size_t) most > first_pass && first_pass < width) {
+        /* never seen; kept so that the result does not rest on the bound */
+        const size_t upto = (size_t) most < width ? (size_t) most : width;
+        code = copy_columns(b, slot, output, soft, out_stride, first_pass, upto - first_pass);
+        if (code != 0) return code;
+        SDRM_CUDA_TRY(cudaStreamSynchronize(b->s_out));
+    }
+    if (output_len != NULL) {
+        memcpy(output_len, b->h_counts, (size_t) b->n_ch * sizeof(uint32_t));
+    }
     b->fetched++;
     return 0;
 }
@@ -736,6 +767,7 @@ void sdrm_fsk_demod_batch_destroy(sdrm_fsk_demod_batch *b) {
     cudaFree(b->d_clock);
     cudaFree(b->d_carry);
     cudaFree(b->d_error);
+    if (b->h_counts != NULL) cudaFreeHost(b->h_counts);
     for (int i = 0; i < 2; i++) {
         cudaFree(b->d_hist1[i]);
         cudaFree(b->d_hist2[i]);

@@ -341,7 +341,14 @@ struct gfsk_mod_t {
     float complex *output;
     size_t output_cap;
     size_t max_bytes;
+    size_t samples_per_byte;
+    size_t locked_bytes; /* prefix of `output` that is page-locked (0: none) */
 };
+
+/* The handle's output buffer is sized for the largest call (258 MB for the reference's perf program, which then sends 2048
+ * bytes at a time): only a prefix is page-locked, so that the results of ordinary calls arrive by DMA instead of through the
+ * driver's staging buffers; a call that needs more gives the lock up. */
+#define LOCKED_OUTPUT_PREFIX ((size_t) 16 << 20)
 
 int gfsk_mod_create(float samples_per_symbol, float sensitivity, float bt, uint32_t max_input_buffer_length, gfsk_mod **mod) {
     struct gfsk_mod_t *result = calloc(1, sizeof(*result));
@@ -354,11 +361,20 @@ int gfsk_mod_create(float samples_per_symbol, float sensitivity, float bt, uint3
         return code;
     }
     result->max_bytes = max_input_buffer_length;
-    result->output_cap = (size_t) max_input_buffer_length * 8 * (size_t) (int) samples_per_symbol;
-    result->output = malloc(sizeof(float complex) * (result->output_cap == 0 ? 1 : result->output_cap));
-    if (result->output == NULL) {
+    result->samples_per_byte = 8 * (size_t) (int) samples_per_symbol;
+    result->output_cap = (size_t) max_input_buffer_length * result->samples_per_byte;
+    const size_t output_bytes = sizeof(float complex) * (result->output_cap == 0 ? 1 : result->output_cap);
+    void *buffer = NULL;
+    if (posix_memalign(&buffer, 4096, output_bytes) != 0) {
         gfsk_mod_destroy(result);
         return -ENOMEM;
+    }
+    result->output = buffer;
+    const size_t prefix = output_bytes < LOCKED_OUTPUT_PREFIX ? output_bytes : LOCKED_OUTPUT_PREFIX;
+    if (cudaHostRegister(result->output, prefix, cudaHostRegisterPortable) == cudaSuccess) {
+        result->locked_bytes = prefix;
+    } else {
+        (void) cudaGetLastError(); /* pageable it stays */
     }
     *mod = result;
     return 0;
@@ -366,6 +382,10 @@ int gfsk_mod_create(float samples_per_symbol, float sensitivity, float bt, uint3
 
 void gfsk_mod_process(const uint8_t *input, size_t input_len, float complex **output, size_t *output_len, gfsk_mod *mod) {
     size_t produced = 0;
+    if (mod->locked_bytes != 0 && input_len <= mod->max_bytes && input_len * mod->samples_per_byte * sizeof(float complex) > mod->locked_bytes) {
+        cudaHostUnregister(mod->output); /* one copy must not straddle locked and pageable memory */
+        mod->locked_bytes = 0;
+    }
     if (sdrm_gfsk_mod_batch_process(mod->batch, input, mod->max_bytes, input_len, mod->output, mod->output_cap, &produced) != 0) {
         *output = NULL;
         *output_len = 0;
@@ -380,6 +400,9 @@ void gfsk_mod_destroy(gfsk_mod *mod) {
         return;
     }
     sdrm_gfsk_mod_batch_destroy(mod->batch);
+    if (mod->locked_bytes != 0) {
+        cudaHostUnregister(mod->output);
+    }
     free(mod->output);
     free(mod);
 }
