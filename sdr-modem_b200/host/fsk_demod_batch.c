@@ -467,6 +467,9 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
      * (clock_recovery_mm.c:101-125), and it has this call's rows plus what it carried (less than 8 + 2 omega) to move over:
      * the fetch copies this many columns and looks at the counts before it trusts the bound */
     b->slot_bound[slot] = (size_t) (((double) n_rows + 16.0 + 2.0 * (b->omega_mid + b->omega_lim)) / (b->omega_mid - b->omega_lim)) + 4;
+    if (b->aid & SDRM_AID_FETCH_BOUND_1) {
+        b->slot_bound[slot] = 1;
+    }
     SDRM_CUDA_TRY(cudaEventRecord(b->ev_tail[slot], b->s_tail));
     b->head += n_rows;
     b->submitted++;

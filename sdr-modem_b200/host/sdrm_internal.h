@@ -53,6 +53,7 @@ static inline int sdrm_launch_code(int code, const char *what) {
  * sdrm_debug_set_measurement_aid, which no installed header declares. */
 #define SDRM_AID_NO_CLOCK_LOOP 1u /* the tail runs, the clock loop emits nothing */
 #define SDRM_AID_NO_TAIL 2u       /* filters only */
+#define SDRM_AID_FETCH_BOUND_1 4u /* test aid, results stay valid: the fetch assumes one symbol per call, so that its second pass runs */
 struct sdrm_fsk_demod_batch_t;
 int sdrm_debug_set_measurement_aid(struct sdrm_fsk_demod_batch_t *batch, uint32_t mask);
 

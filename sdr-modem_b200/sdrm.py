@@ -18,6 +18,7 @@ MAX_IN_FLIGHT = 2
 # measurement aids (host/sdrm_internal.h): results become invalid; tools/probe_*.py and bench.py --debug-no-tail only
 AID_NO_CLOCK_LOOP = 1
 AID_NO_TAIL = 2
+AID_FETCH_BOUND_1 = 4
 
 
 class FskDemodBatchConfig(C.Structure):

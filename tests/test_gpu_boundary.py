@@ -106,6 +106,40 @@ def test_fetch_with_soft_pointer_but_no_soft_flag_leaves_the_call_unfetched(sdrm
     b.close()
 
 
+def test_fetch_moves_only_what_a_call_can_have_produced_and_survives_a_wrong_bound(sdrm, port):
+    """A handle created for 2016000-sample buffers (what test/perf_fsk_modem.c does) and fed 4096 samples copies a bounded
+    number of columns back, not its whole capacity; the counts that come back with them are checked against the bound, and when
+    they exceed it (forced here through the test aid) the rest follows in a second pass. Both ways the symbols are the oracle's,
+    and nothing outside the produced prefix of the caller's buffer is touched."""
+    _, _, args = FSK_GOLDENS["lucky7"]
+    iq = golden_array("lucky7.expected.cf32", np.complex64)
+    chunk = 4096
+    o_hard, o_soft = port.FskDemod(*args, 2016000).run(iq, chunk)
+    for aid in (0, sdrm.AID_FETCH_BOUND_1):
+        b = sdrm.FskDemodBatch(3, *args, 2016000, soft=True, measurement_aid=aid)
+        hard = np.full((3, 2016000), 77, np.int8)
+        soft = np.full((3, 2016000), 7.0, np.float32)
+        lens = np.zeros(3, np.uint32)
+        parts = [[] for _ in range(3)]
+        soft_parts = [[] for _ in range(3)]
+        most = 0
+        for o in range(0, len(iq), chunk):
+            block = np.ascontiguousarray(np.broadcast_to(iq[o:o + chunk], (3, len(iq[o:o + chunk]))))
+            b.submit(block)
+            b.fetch(hard=hard, lens=lens, soft=soft)
+            for c in range(3):
+                parts[c].append(hard[c, :lens[c]].copy())
+                soft_parts[c].append(soft[c, :lens[c]].copy())
+            most = max(most, int(lens.max()))
+        assert b.error_flags() == 0
+        b.close()
+        for c in range(3):
+            assert same_bits(np.concatenate(parts[c]), o_hard) and same_bits(np.concatenate(soft_parts[c]), o_soft), (aid, c)
+        # 4096 samples / decimation 2 / 5 samples per symbol: about 410 symbols; the bound adds a few columns, not megabytes
+        assert 300 < most < 600
+        assert (hard[:, 1024:] == 77).all() and (soft[:, 1024:] == 7.0).all()
+
+
 class RawCuda:
     """a device pointer as something torch.as_tensor can view without copying"""
 
