@@ -785,7 +785,11 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
         return -(int) err - 1000;
     }
     // two 32-row blocks per step where everything is long enough for 64-row steps and the tiles fit in shared memory
+#ifdef TAIL_FORCE_SB  // A/B builds (tools/ab_build.sh)
+    int sb = TAIL_FORCE_SB;
+#else
     int sb = 2;
+#endif
     size_t smem = 0;
     for (; sb >= 1; sb--) {
         const size_t tiles = (size_t) (prod - 1) * 2 + 2 + (size_t) prod * 2 + 2;
