@@ -66,6 +66,8 @@ def load():
     lib.orc_bench_fsk_demod.restype = C.c_double
     lib.orc_bench_fsk_demod.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_uint8, C.c_uint32, C.c_int, C.c_uint32,
                                         vp, sz, sz, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    lib.orc_sincos_sweep.restype = sz
+    lib.orc_sincos_sweep.argtypes = [C.c_uint32, sz, vp, C.POINTER(C.c_uint32)]
     lib.free = C.CDLL(None).free
     lib.free.argtypes = [vp]
     _lib = lib
@@ -299,3 +301,25 @@ def bench_fsk_demod(fs, baud, deviation, decimation, tw, use_dc, chunk, iq_chann
     if sec < 0:
         raise ValueError("orc_bench_fsk_demod failed")
     return sec, sym.value
+
+
+def sincos_sweep(first_bits, got, threads=16):
+    """got: float32 array [count][2] of (cos, sin) for the float bit patterns first_bits ...; returns (number of values that
+    differ from libm's double cos / sin rounded to float, first differing pattern or None). Split over threads (ctypes
+    releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib = load()
+    got = np.ascontiguousarray(got, dtype=np.float32)
+    count = got.shape[0]
+    edges = np.linspace(0, count, threads + 1).astype(np.int64)
+
+    def part(k):
+        lo, hi = int(edges[k]), int(edges[k + 1])
+        bad_at = C.c_uint32(0)
+        bad = lib.orc_sincos_sweep(first_bits + lo, hi - lo, got[lo:].ctypes.data_as(C.c_void_p), C.byref(bad_at))
+        return bad, bad_at.value
+    with ThreadPoolExecutor(threads) as pool:
+        results = list(pool.map(part, range(threads)))
+    total = sum(r[0] for r in results)
+    first = next((r[1] for r in results if r[0]), None)
+    return total, first

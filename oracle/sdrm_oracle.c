@@ -832,3 +832,26 @@ double orc_bench_fsk_demod(uint64_t fs, uint32_t baud, int64_t deviation, uint8_
     }
     return failed ? -1.0 : (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* libm sweep (tests/test_gpu_sincos_sweep.py): (float) cos((double) x) and (float) sin((double) x) — what
+ * frequency_modulator.c:56 and sig_source.c store for a float phase — for the floats with bit patterns
+ * [first_bits, first_bits + count), compared bit for bit with `got` ((cos, sin) pairs computed elsewhere).
+ * Returns the number of values that differ; *first_bad = the first pattern with a difference. */
+size_t orc_sincos_sweep(uint32_t first_bits, size_t count, const float *got, uint32_t *first_bad) {
+    size_t bad = 0;
+    for (size_t i = 0; i < count; i++) {
+        const uint32_t bits = first_bits + (uint32_t) i;
+        float x;
+        memcpy(&x, &bits, sizeof(x));
+        const float c = (float) cos((double) x);
+        const float s = (float) sin((double) x);
+        const int differs = memcmp(&c, &got[2 * i], sizeof(float)) != 0 || memcmp(&s, &got[2 * i + 1], sizeof(float)) != 0;
+        if (differs) {
+            if (bad == 0 && first_bad != NULL) {
+                *first_bad = bits;
+            }
+            bad++;
+        }
+    }
+    return bad;
+}

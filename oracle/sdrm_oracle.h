@@ -100,4 +100,8 @@ double orc_bench_fsk_demod(uint64_t fs, uint32_t baud, int64_t deviation, uint8_
                            uint32_t chunk, const float *iq, size_t stride_floats, size_t n_samples, int n_channels,
                            int n_threads, int passes, uint64_t *symbols_out);
 
+/* libm sweep over float bit patterns [first_bits, first_bits + count): counts the (cos, sin) pairs in `got` that differ from
+ * (float) cos((double) x), (float) sin((double) x) */
+size_t orc_sincos_sweep(uint32_t first_bits, size_t count, const float *got, uint32_t *first_bad);
+
 #endif

@@ -52,4 +52,9 @@ __device__ __forceinline__ float sdrm_quad_demod_sample(float2 cur, float2 prev,
     return __fmul_rn(gain, sdrm_fast_atan2f(im, re, table));
 }
 
+// (float) cos((double) p), (float) sin((double) p): what the reference's frequency modulator and signal source store for a
+// float phase (frequency_modulator.c:56, sig_source.c). One definition for every kernel that needs it, so that the sweep over
+// all float phases (sdrm_cu_selftest_sincos, tests/test_gpu_sincos_sweep.py) checks the code that runs.
+__device__ __forceinline__ void sdrm_phase_sincos(float p, double *sin_out, double *cos_out) { sincos((double) p, sin_out, cos_out); }
+
 #endif

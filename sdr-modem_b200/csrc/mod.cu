@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "device_math.cuh"
 #include "sdrm_cuda.h"
 
 namespace {
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(256) phase_to_iq_kernel(const float *__restric
             if (m < n && ch < n_ch) {
                 double s;
                 double co;
-                sincos((double) tile[lane][c], &s, &co);
+                sdrm_phase_sincos(tile[lane][c], &s, &co);
                 out[(size_t) ch * out_stride + m] = make_float2((float) co, (float) s);
             }
         }
@@ -359,7 +360,32 @@ __global__ void __launch_bounds__(256) phase_to_iq_kernel(const float *__restric
     }
 }
 
+// self test: the (cos, sin) pairs the modulator stores for the floats with bit patterns [first_bits, first_bits + count)
+__global__ void sincos_selftest_kernel(uint32_t first_bits, size_t count, float2 *out) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x) {
+        double s;
+        double co;
+        sdrm_phase_sincos(__uint_as_float(first_bits + (uint32_t) i), &s, &co);
+        out[i] = make_float2((float) co, (float) s);
+    }
+}
+
 }  // namespace
+
+extern "C" int sdrm_cu_selftest_sincos(uint32_t first_bits, size_t count, float *h_cos_sin) {
+    if (count == 0) {
+        return 0;
+    }
+    float2 *d = nullptr;
+    if (cudaMalloc(&d, count * sizeof(float2)) != cudaSuccess) {
+        (void) cudaGetLastError();
+        return -12;
+    }
+    sincos_selftest_kernel<<<148 * 8, 256>>>(first_bits, count, d);
+    cudaError_t err = cudaMemcpy(h_cos_sin, d, count * sizeof(float2), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return err == cudaSuccess ? 0 : -(int) err - 1000;
+}
 
 extern "C" int sdrm_cu_interp_fir(const sdrm_interp_args *a, void *stream_ptr) {
     if (a->n_ch <= 0) {

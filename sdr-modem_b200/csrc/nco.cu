@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "device_math.cuh"
 #include "sdrm_cuda.h"
 
 namespace {
@@ -110,7 +111,7 @@ __global__ void nco_rotate_kernel(const float2 *__restrict__ in, size_t in_strid
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             double s;
             double c;
-            sincos((double) ph[i], &s, &c);
+            sdrm_phase_sincos(ph[i], &s, &c);
             const float cr = (float) (c * amp);
             const float ci = (float) (s * amp);
             if (MULTIPLY) {

@@ -170,6 +170,8 @@ int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream);
 
 /* Self test (synchronous): counts sums for which the tail's branch-free division by `length` differs from an IEEE
  * division, over blocks * 256 * per_thread pseudo-random values. Used by tests only. */
+/* (cos, sin) as the modulator stores them for the float bit patterns [first_bits, first_bits + count); h_cos_sin: 2 * count floats */
+int sdrm_cu_selftest_sincos(uint32_t first_bits, size_t count, float *h_cos_sin);
 int sdrm_cu_selftest_div(int length, int steps, uint32_t seed, int blocks, int per_thread, unsigned long long *mismatches);
 
 /*

@@ -229,3 +229,19 @@ def test_sample_format_converts_match_reference_kats(port):
     assert np.array_equal(tx, np.arange(50, dtype=np.int16) * 16)
     edge = np.array([1.0, -1.0, 2.0, -2.0, 0.5 / 32768, 1.5 / 32768, 2.5 / 32768, -0.5 / 32768, np.nan], dtype=np.float32)
     assert list(port.convert_32f_16i(edge, 32768.0)) == [32767, -32768, 32767, -32768, 0, 2, 2, 0, 0]
+
+
+def test_libm_sweep_counts_one_ulp_differences(port):
+    """the checker behind tests/test_gpu_sincos_sweep.py: agrees with numpy's double cos / sin on a block of float phases and
+    counts exactly the values that were moved by one ulp"""
+    from oracle import port as port_module
+    first, n = 0x40000000, 1 << 18   # floats from 2.0 upwards
+    x = (np.arange(n, dtype=np.uint32) + first).view(np.float32).astype(np.float64)
+    got = np.stack([np.cos(x).astype(np.float32), np.sin(x).astype(np.float32)], axis=1)
+    clean, _ = port_module.sincos_sweep(first, got, threads=4)
+    assert clean <= 2  # numpy's SIMD routines may differ from libm in the last place of a rare value; libm is the reference
+    moved = got.copy()
+    moved[12345, 1] = np.nextafter(moved[12345, 1], np.float32(2))
+    moved[200000, 0] = np.nextafter(moved[200000, 0], np.float32(2))
+    bad, where = port_module.sincos_sweep(first, moved, threads=4)
+    assert clean + 1 <= bad <= clean + 2 and where is not None
