@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, same_bits
 
 HEADERS = sorted(glob.glob(os.path.join(ROOT, "include", "sdrm", "*.h")))
 DECL = re.compile(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?[\s\*](\w+)\s*\([^;{]*\)\s*;", re.M | re.S)
@@ -82,6 +82,48 @@ def test_host_tap_design_matches_oracle(sdrm, port):
     p, n = C.POINTER(C.c_float)(), C.c_size_t()
     for bad in ((0, 1750, 500), (8000, 5000, 500), (8000, 1750, 0)):  # reference test/test_lpf_taps.c bounds
         assert lib.create_low_pass_filter(1.0, *bad, C.byref(p), C.byref(n)) == -1
+
+
+def test_host_tap_design_matches_reference_over_random_parameters(sdrm, port):
+    """300 random (sampling rate, cutoff, transition width) triples across the range fsk_demod_create and dsp_worker derive
+    (8 kHz ... 10 MHz, 3 ... 20000 taps), and Gaussian taps for random samples-per-symbol: the product's host code against
+    the reference build where it is present, else the restatement (which tests/test_oracle.py pins to the reference)."""
+    from oracle import ref
+    lib = sdrm.lib
+    lib.create_low_pass_filter.argtypes = [C.c_float, C.c_uint64, C.c_uint64, C.c_uint32,
+                                           C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t)]
+    lib.gaussian_taps_create.argtypes = [C.c_double, C.c_double, C.c_double, C.c_size_t, C.POINTER(C.POINTER(C.c_float))]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    want_lpf = ref.lpf_taps if ref.available() else port.low_pass_taps
+    want_gauss = ref.gaussian_taps if ref.available() else port.gaussian_taps
+    rng = np.random.default_rng(2024)
+    lengths = []
+    for _ in range(300):
+        fs = int(10 ** rng.uniform(np.log10(8000), 7))
+        cutoff = int(fs * rng.uniform(0.002, 0.45))
+        tw = max(1, int(fs * 10 ** rng.uniform(-3.6, -0.7)))
+        gain = float(np.float32(rng.choice([1.0, 0.5, 2.25])))
+        p, n = C.POINTER(C.c_float)(), C.c_size_t()
+        code = lib.create_low_pass_filter(gain, fs, cutoff, tw, C.byref(p), C.byref(n))
+        if code != 0:
+            with pytest.raises(Exception):
+                want_lpf(gain, fs, cutoff, tw)
+            continue
+        taps = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+        libc.free(p)
+        assert same_bits(taps, want_lpf(gain, fs, cutoff, tw)), (gain, fs, cutoff, tw)
+        lengths.append(len(taps))
+    assert len(lengths) > 250 and min(lengths) < 20 and max(lengths) > 5000
+    for _ in range(100):
+        sps = float(rng.uniform(1.5, 40.0))
+        bt = float(rng.choice([0.3, 0.5, 1.0]))
+        ntaps = int(rng.integers(2, 200))
+        p = C.POINTER(C.c_float)()
+        assert lib.gaussian_taps_create(1.0, sps, bt, ntaps, C.byref(p)) == 0
+        taps = np.ctypeslib.as_array(p, shape=(ntaps,)).copy()
+        libc.free(p)
+        assert same_bits(taps, want_gauss(1.0, sps, bt, ntaps)), (sps, bt, ntaps)
 
 
 def test_host_fast_atan2f_matches_oracle(sdrm, port):
