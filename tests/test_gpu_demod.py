@@ -247,3 +247,62 @@ def test_tail_division_by_length_is_ieee(sdrm, length, steps):
     bad = C.c_ulonglong(123)
     assert lib.sdrm_cu_selftest_div(length, steps, 12345 + length, 1184, 4096, C.byref(bad)) == 0
     assert bad.value == 0
+
+
+# ---- random parameter sets ------------------------------------------------------------------------------------------------
+def random_demod_config(seed):
+    rng = np.random.default_rng(5000 + seed)
+    dec = int(rng.choice([1, 2, 2, 3, 4, 5, 6, 8]))
+    sps_out = float(rng.uniform(2.0, 24.0))
+    baud = int(rng.choice([1000, 1200, 2400, 4800, 7777, 9600, 19200]))
+    fs = int(round(baud * sps_out * dec)) + int(rng.integers(0, 7))
+    deviation = int(baud * rng.uniform(0.25, 1.5)) * (1 if rng.random() < 0.8 else -1)
+    tw = max(50, int(baud * rng.uniform(0.05, 0.5)))
+    use_dc = bool(rng.random() < 0.7)
+    return rng, (fs, baud, deviation, dec, tw, use_dc)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_parameter_sets_bit_exact(sdrm, port, seed):
+    """fsk_demod_create's whole parameter space, sampled: decimation 1..8, 2..24 samples per symbol (non-integer), either sign of
+    the deviation, filters from a few dozen to several thousand taps (one tap block, several, and the multi-launch path), dc
+    blocker on and off; even seeds run a fixed call size (compared with the restatement AND the reference build), odd seeds a
+    ragged sequence of call sizes with empty and tiny calls in it. A parameter set the reference rejects must be rejected."""
+    rng, args = random_demod_config(seed)
+    fs, baud, deviation, dec, tw, use_dc = args
+    n = 30000
+    shape = workloads.DemodShape("random", fs, baud, abs(deviation), dec, tw, use_dc, 4096)
+    iq = workloads.gfsk_channels(3, n, shape, seed=300 + seed).numpy()
+    try:
+        probe = port.FskDemod(*args, 4096)
+    except Exception:
+        with pytest.raises(sdrm.SdrmError):
+            sdrm.FskDemodBatch(3, *args, 4096)
+        return
+    del probe
+    if seed % 2 == 0:
+        chunk = int(rng.choice([1024, 4096, 5000, 30000]))
+        hard, soft = gpu_chain(sdrm, args, iq, chunk)
+        for c in range(3):
+            oh, os_ = oracle_chain(port, args, iq[c], chunk)
+            assert len(oh) > 0.8 * n / (fs / baud) - 20
+            assert same_bits(hard[c], oh) and same_bits(soft[c], os_), (args, chunk, c)
+        return
+    sizes = []
+    while sum(sizes) < n:
+        sizes.append(int(rng.choice([0, 1, 3, 17, 500, 2048, 4095, 6000])))
+    sizes[-1] -= sum(sizes) - n
+    b = sdrm.FskDemodBatch(3, *args, 6000, soft=True)
+    oracles = [port.FskDemod(*args, 6000) for _ in range(3)]
+    off = 0
+    try:
+        for size in sizes:
+            part = iq[:, off:off + size]
+            off += size
+            hard, lens, soft = b.process(np.ascontiguousarray(part))
+            for c in range(3):
+                oh, os_ = oracles[c].process(part[c])
+                assert same_bits(hard[c, :lens[c]], oh) and same_bits(soft[c, :lens[c]], os_), (args, sizes, c)
+        assert b.error_flags() == 0
+    finally:
+        b.close()

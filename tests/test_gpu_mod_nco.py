@@ -59,6 +59,37 @@ def test_gfsk_mod_batch_vs_oracle(sdrm, port, sps):
     b.close()
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_gfsk_mod_random_parameter_sets(sdrm, port, seed):
+    """gfsk_mod_create's parameter space, sampled: 2..40 samples per symbol (fractional values truncate as in
+    src/dsp/gfsk_mod.c:85), BT 0.3 / 0.5 / 1.0, sensitivities from small to more than pi / 2 per sample (frequent phase wraps),
+    1..70 channels (partial and several 32-channel groups), packets of random lengths incl. empty ones with carried phase and
+    filter history. Sets the reference rejects must be rejected."""
+    rng = np.random.default_rng(900 + seed)
+    sps = float(rng.choice([2.0, 2.0, 3.0, 4.0, 5.5, 8.0, 10.0, 20.0, 33.0, 40.0]))
+    bt = float(rng.choice([0.3, 0.5, 1.0]))
+    sens = float(np.float32(rng.uniform(0.01, 2.2)))
+    n_ch = int(rng.choice([1, 2, 31, 32, 33, 70]))
+    max_bytes = 300
+    try:
+        oracles = [port.GfskMod(sps, sens, bt, max_bytes) for _ in range(n_ch)]
+    except ValueError:
+        with pytest.raises(sdrm.SdrmError):
+            sdrm.GfskModBatch(n_ch, sps, sens, bt, max_bytes)
+        return
+    b = sdrm.GfskModBatch(n_ch, sps, sens, bt, max_bytes)
+    try:
+        for _ in range(6):
+            n = int(rng.choice([0, 1, 2, 7, 64, 255, 300]))
+            data = rng.integers(0, 256, (n_ch, n), dtype=np.uint8)
+            got = b.process(data)
+            for c in range(n_ch):
+                want = oracles[c].process(data[c])
+                assert got[c].shape == want.shape and close_trig(got[c], want), (sps, bt, sens, n_ch, n, c)
+    finally:
+        b.close()
+
+
 def test_gfsk_mod_perf_shape_packets(sdrm, port):
     """BASELINE config 4 shape: sps 2, 2048-byte packets, bytes (uint8) i (reference test/perf_fsk_modem.c:23-38)"""
     sps, sens = 2.0, float(np.float32(2 * np.pi * 5000 / 19200))
