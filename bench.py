@@ -576,6 +576,7 @@ def main():
     ms_total = max_over_ranks(start.elapsed_time(end))
     launches = int(batch.launch_count - launches_before)
     symbols_last = int(pin_len[0].array.sum())
+    fetched_columns = int(batch.last_fetch_columns())
 
     # per-kernel times of the dominant kernel, CUDA events on its own stream, inside a (second) timed loop
     batch.set_profiling(True)
@@ -663,7 +664,9 @@ def main():
         del scratch
         e2e_value = samples_per_step * e2e_steps / e2e_s / 1e6
         e2e = {"value": e2e_value, "unit": UNIT,
-               "h2d_bytes_per_step": world * n_ch * chunk * 8, "d2h_bytes_per_step": world * (n_ch * cap + n_ch * 4),
+               "h2d_bytes_per_step": world * n_ch * chunk * 8,
+               # what a fetch moves: the columns a call of this size can fill (the library's bound), not the rows' capacity
+               "d2h_bytes_per_step": world * (n_ch * batch.last_fetch_columns() + n_ch * 4),
                "steps": e2e_steps, "symbols_last_step": symbols,
                "h2d_gbs": e2e_value * 8e6 / 1e9,
                "h2d_ceiling_gbs": ceiling_gbs, "h2d_ceiling_sum_of_ranks_gbs": sum_gbs,
@@ -786,7 +789,8 @@ def main():
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "value_includes": "int8 symbols + counts copied to pinned host memory every step (%d B per step)" % (n_ch * cap + n_ch * 4),
+        "value_includes": "int8 symbols + counts copied to pinned host memory every step (%d B per step)"
+                          % (n_ch * fetched_columns + n_ch * 4),
         "symbols_last_step": symbols_last,
         "realtime_channels_per_gpu": value / world * 1e6 / shape.sampling_freq,
         "input_gen_s": gen_s, "host_cpus_near_gpu": local_cpus,

@@ -113,6 +113,9 @@ void *sdrm_fsk_demod_batch_out_stream(sdrm_fsk_demod_batch *batch);
 
 /* Number of kernels launched by this batch since creation (bench.py reports it as gpu_launches). */
 uint64_t sdrm_fsk_demod_batch_launch_count(const sdrm_fsk_demod_batch *batch);
+/* Columns (symbols) per channel the last fetch copied to the host: the most a call of that many samples can produce, not the
+ * whole capacity of the result rows. For byte accounting. */
+size_t sdrm_fsk_demod_batch_last_fetch_columns(const sdrm_fsk_demod_batch *batch);
 
 /*
  * Optional per-stage timing with CUDA events on the launching streams. stage_times synchronises and returns, for the

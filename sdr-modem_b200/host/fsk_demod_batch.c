@@ -100,6 +100,7 @@ struct sdrm_fsk_demod_batch_t {
     size_t out_stride;
     size_t slot_bound[SLOTS]; /* most symbols the clock loop can produce from the rows of the call in this slot */
     uint32_t *h_counts;       /* pinned, one per channel: the symbol counts of the call being fetched */
+    size_t last_fetch_columns; /* columns per channel the last fetch moved */
     cudaEvent_t ev_fir[SLOTS];
     cudaEvent_t ev_tail[SLOTS];
     cudaEvent_t ev_copy[SLOTS];
@@ -632,6 +633,7 @@ int sdrm_fsk_demod_batch_fetch(sdrm_fsk_demod_batch *b, int8_t *output, float *s
     if (output_len != NULL) {
         memcpy(output_len, b->h_counts, (size_t) b->n_ch * sizeof(uint32_t));
     }
+    b->last_fetch_columns = (size_t) most > first_pass && first_pass < width ? ((size_t) most < width ? (size_t) most : width) : first_pass;
     b->fetched++;
     return 0;
 }
@@ -737,6 +739,8 @@ int sdrm_debug_set_measurement_aid(sdrm_fsk_demod_batch *b, uint32_t mask) {
 }
 
 uint64_t sdrm_fsk_demod_batch_launch_count(const sdrm_fsk_demod_batch *b) { return b == NULL ? 0 : b->launches; }
+
+size_t sdrm_fsk_demod_batch_last_fetch_columns(const sdrm_fsk_demod_batch *b) { return b == NULL ? 0 : b->last_fetch_columns; }
 
 int sdrm_fsk_demod_batch_error_flags(sdrm_fsk_demod_batch *b) {
     if (b == NULL) {

@@ -73,6 +73,8 @@ def _load():
     lib.sdrm_debug_set_measurement_aid.argtypes = [vp, C.c_uint32]
     lib.sdrm_fsk_demod_batch_launch_count.restype = C.c_uint64
     lib.sdrm_fsk_demod_batch_launch_count.argtypes = [vp]
+    lib.sdrm_fsk_demod_batch_last_fetch_columns.restype = C.c_size_t
+    lib.sdrm_fsk_demod_batch_last_fetch_columns.argtypes = [vp]
     lib.sdrm_fsk_demod_batch_error_flags.argtypes = [vp]
     lib.sdrm_fsk_demod_batch_set_profiling.argtypes = [vp, i32]
     lib.sdrm_fsk_demod_batch_stage_times.argtypes = [vp, C.POINTER(C.c_float)]
@@ -307,6 +309,9 @@ class FskDemodBatch:
     @property
     def launch_count(self):
         return lib.sdrm_fsk_demod_batch_launch_count(self.handle)
+
+    def last_fetch_columns(self):
+        return lib.sdrm_fsk_demod_batch_last_fetch_columns(self.handle)
 
     def set_profiling(self, enabled=True):
         _check(lib.sdrm_fsk_demod_batch_set_profiling(self.handle, int(enabled)), "sdrm_fsk_demod_batch_set_profiling")
