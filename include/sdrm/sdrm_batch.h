@@ -46,7 +46,7 @@ typedef struct {
 /*
  * Parameter ranges narrower than the reference's fsk_demod_create (the fused serial tail keeps one symbol step plus one
  * 32-row block of every channel in shared memory); create logs the reason and returns -1 outside them:
- *   samples per symbol after decimation, sps = sampling_freq / baud_rate / decimation:  1 <= sps <= 900
+ *   samples per symbol after decimation, sps = sampling_freq / baud_rate / decimation:  1 <= sps <= 855
  *   with use_dc_block: dc blocker length ceil(32 * sps) >= 32, i.e. sps >= 1 (the reference accepts fractional sps < 1,
  *   which no FSK receiver can use).
  * Batches of more than 65535 channels are accepted (kernels that index rows with gridDim.y loop over the remainder).
