@@ -44,11 +44,14 @@ typedef struct {
 } sdrm_fsk_demod_batch_config;
 
 /*
- * Parameter ranges narrower than the reference's fsk_demod_create (the fused serial tail keeps one symbol step plus one
- * 32-row block of every channel in shared memory); create logs the reason and returns -1 outside them:
- *   samples per symbol after decimation, sps = sampling_freq / baud_rate / decimation:  1 <= sps <= 855
- *   with use_dc_block: dc blocker length ceil(32 * sps) >= 32, i.e. sps >= 1 (the reference accepts fractional sps < 1,
- *   which no FSK receiver can use).
+ * Parameter ranges against the reference's fsk_demod_create. With sps = sampling_freq / baud_rate / decimation (samples per
+ * symbol after decimation):
+ *   sps <= 855   the fused serial tail (one kernel: dc blocker + clock recovery, one symbol step of every channel in shared
+ *                memory);
+ *   sps >  855   accepted like the reference does, served by two plain kernels (dc blocker, clock loop) on the lpf2 output
+ *                ring: same results, a slower tail;
+ *   with use_dc_block the dc blocker length ceil(32 * sps) must be >= 32, i.e. sps >= 1: create logs the reason and returns
+ *                -1 below that (the reference accepts fractional sps < 1, which no FSK receiver can use).
  * Batches of more than 65535 channels are accepted (kernels that index rows with gridDim.y loop over the remainder).
  */
 int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_fsk_demod_batch **batch);

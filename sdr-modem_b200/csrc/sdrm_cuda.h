@@ -89,7 +89,7 @@ int sdrm_cu_quad_demod(const void *in, size_t in_stride, void *prev, float gain,
  * identical for all channels and advanced by the caller (pos + n_rows modulo the line length).
  */
 int sdrm_cu_dc_blocker(float *ring, size_t tc_stride, int ring_rows, long long head, int n_rows, int n_ch, int length,
-                       float *delay, float *sums, int pos_l, int pos_x, void *stream);
+                       float *delay, float *sums, int pos_l, int pos_x, int grouped, void *stream);
 
 /*
  * Mueller & Mueller clock recovery + int8 conversion (reference src/dsp/clock_recovery_mm.c:78-139,
@@ -123,6 +123,7 @@ typedef struct {
     int max_out;       /* reference output_len: the loop stops after this many symbols */
     int *error_flag;   /* device int; bit 0 set if a channel's carried history exceeded max_history */
     int fast;          /* 1: the 8-tap interpolator dot product uses fused multiply-add */
+    int grouped;       /* 0: ring[row][tc_stride]; 1: the grouped layout of the decimating FIR, ring[ch / 32][row][32] */
 } sdrm_clock_args;
 
 int sdrm_cu_clock_mm(const sdrm_clock_args *args, void *stream);

@@ -24,8 +24,20 @@ __device__ __forceinline__ float ma_step(float x, float delayed, float &sum, flo
     return __fdiv_rn(sum, length_f);
 }
 
+// Channel ch's column of the ring: ring[row][tc_stride] (per-block handles) or, grouped, the layout the decimating FIR writes
+// for the batch, ring[ch / 32][row][32]. Returns the column's first element; rows are `stride` floats apart.
+__device__ __forceinline__ float *ring_column(float *ring, size_t tc_stride, int ring_rows, int ch, int grouped, size_t *stride) {
+    if (grouped) {
+        *stride = 32;
+        return ring + (size_t) (ch >> 5) * (size_t) ring_rows * 32 + (ch & 31);
+    }
+    *stride = tc_stride;
+    return ring + ch;
+}
+
 __global__ void dc_blocker_kernel(float *ring, size_t tc_stride, int ring_mask, long long head, int n_rows, int n_ch,
-                                  int length, float *__restrict__ delay, float *__restrict__ sums, int pos_l, int pos_x) {
+                                  int length, float *__restrict__ delay, float *__restrict__ sums, int pos_l, int pos_x,
+                                  int grouped) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_ch) {
         return;
@@ -45,8 +57,10 @@ __global__ void dc_blocker_kernel(float *ring, size_t tc_stride, int ring_mask, 
 
     int pl = pos_l;
     int px = pos_x;
+    size_t stride;
+    float *column = ring_column(ring, tc_stride, ring_mask + 1, ch, grouped, &stride);
     for (int n = 0; n < n_rows; n++) {
-        float *cell = ring + (size_t) ((head + n) & ring_mask) * tc_stride + ch;
+        float *cell = column + (size_t) ((head + n) & ring_mask) * stride;
         const size_t ol = (size_t) pl * n_ch;
         const size_t ox = (size_t) px * n_ch;
         const float x = *cell;
@@ -98,7 +112,8 @@ __global__ void clock_mm_kernel(const sdrm_clock_args a) {
         return;
     }
     const unsigned long long max_index = (unsigned long long) (working_len - 7);
-    const float *col = a.ring + ch;
+    size_t stride;
+    const float *col = ring_column(const_cast<float *>(a.ring), a.tc_stride, a.ring_rows, ch, a.grouped, &stride);
     float *soft = a.soft_out != nullptr ? a.soft_out + (size_t) ch * a.out_stride : nullptr;
     int8_t *hard = a.hard_out != nullptr ? a.hard_out + (size_t) ch * a.out_stride : nullptr;
 
@@ -117,12 +132,12 @@ __global__ void clock_mm_kernel(const sdrm_clock_args a) {
         const int lead = ii & 3;
         float acc = 0.0f;
         for (int k = lead; k > 0; k--) {
-            const float v = col[(size_t) ((base + ii - k) & ring_mask) * a.tc_stride];
+            const float v = col[(size_t) ((base + ii - k) & ring_mask) * stride];
             acc = a.fast ? __fmaf_rn(v, 0.0f, acc) : __fadd_rn(acc, __fmul_rn(v, 0.0f));
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const float v = col[(size_t) ((base + ii + k) & ring_mask) * a.tc_stride];
+            const float v = col[(size_t) ((base + ii + k) & ring_mask) * stride];
             acc = a.fast ? __fmaf_rn(v, t[7 - k], acc) : __fadd_rn(acc, __fmul_rn(v, t[7 - k]));
         }
         float out = acc;
@@ -167,7 +182,7 @@ __global__ void clock_mm_kernel(const sdrm_clock_args a) {
 }  // namespace
 
 extern "C" int sdrm_cu_dc_blocker(float *ring, size_t tc_stride, int ring_rows, long long head, int n_rows, int n_ch,
-                                  int length, float *delay, float *sums, int pos_l, int pos_x, void *stream_ptr) {
+                                  int length, float *delay, float *sums, int pos_l, int pos_x, int grouped, void *stream_ptr) {
     if (n_rows <= 0 || n_ch <= 0) {
         return 0;
     }
@@ -176,7 +191,7 @@ extern "C" int sdrm_cu_dc_blocker(float *ring, size_t tc_stride, int ring_rows, 
     }
     const int threads = 32;
     dc_blocker_kernel<<<(n_ch + threads - 1) / threads, threads, 0, (cudaStream_t) stream_ptr>>>(
-        ring, tc_stride, ring_rows - 1, head, n_rows, n_ch, length, delay, sums, pos_l, pos_x);
+        ring, tc_stride, ring_rows - 1, head, n_rows, n_ch, length, delay, sums, pos_l, pos_x, grouped);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }

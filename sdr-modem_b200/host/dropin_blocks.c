@@ -493,7 +493,7 @@ void dc_blocker_process(float *input, size_t input_len, float **output, size_t *
     d->head = 0;
     int ok = cudaMemcpyAsync(d->d_ring, d->h_pack, input_len * 8, cudaMemcpyHostToDevice, d->stream) == cudaSuccess;
     ok = ok && sdrm_launch_code(sdrm_cu_dc_blocker(d->d_ring, 2, (int) d->ring_rows, 0, (int) input_len, 2, d->length, d->d_delay,
-                                                   d->d_sums, d->pos_l, d->pos_x, d->stream),
+                                                   d->d_sums, d->pos_l, d->pos_x, 0, d->stream),
                                 "dc blocker") == 0;
     ok = ok && cudaMemcpyAsync(d->h_pack, d->d_ring, input_len * 8, cudaMemcpyDeviceToHost, d->stream) == cudaSuccess;
     ok = ok && sdrm_cuda_code(cudaStreamSynchronize(d->stream), "dc_blocker_process") == 0;

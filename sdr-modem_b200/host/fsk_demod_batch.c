@@ -88,6 +88,8 @@ struct sdrm_fsk_demod_batch_t {
     sdrm_clock_state *d_clock;
     float *d_carry;
     int ring_slots;
+    int unfused; /* samples per symbol beyond what the fused tail's shared-memory ring holds: dc blocker and clock loop run as
+                    the two plain kernels of tail.cu, straight on the lpf2 output ring */
     int *d_error;
 
     /* staging + results, one set per slot */
@@ -213,6 +215,16 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
     b->tc_stride = b->n_ch_pad;
     code = sdrm_dev_zalloc((void **) &b->d_ring, (size_t) b->ring_rows * b->tc_stride * sizeof(float));
     if (code != 0) goto fail;
+    /* per-lane shared-memory ring of the fused tail: one symbol step + two pipeline steps of 64 rows + slack, power of two */
+    b->ring_slots = (int) sdrm_next_pow2((uint64_t) ceilf(sps * 1.01f) + 8 + 2 * 64 + 16 + 8);
+    if (b->ring_slots < 128) {
+        b->ring_slots = 128;
+    }
+    if (b->ring_slots > 1024) {
+        /* more than ~855 samples per symbol (the reference accepts any): no shared-memory ring, the two-kernel tail */
+        b->unfused = 1;
+        b->ring_slots = 128;
+    }
     if (config->use_dc_block) {
         b->dc_len = (int) ceilf(sps * 32);
         if (b->dc_len < 2) {
@@ -226,7 +238,7 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
         }
         /* group delay line: 2L - 2 rows of delay + the rows the pipeline's first stage writes ahead of its last (4 steps of up
          * to 64 rows), with the same again as head room */
-        b->dx_len = 2 * b->dc_len - 2 + 512;
+        b->dx_len = b->unfused ? 2 * b->dc_len - 2 : 2 * b->dc_len - 2 + 512;
         b->div_steps = sdrm_division_steps(b->dc_len);
         code = sdrm_dev_zalloc((void **) &b->d_delay, ((size_t) 4 * b->dc_len + b->dx_len) * b->n_ch_pad * sizeof(float));
         if (code != 0) goto fail;
@@ -253,16 +265,6 @@ int sdrm_fsk_demod_batch_create(const sdrm_fsk_demod_batch_config *config, sdrm_
                               "clock state upload");
         free(init);
         if (code != 0) goto fail;
-    }
-    /* per-lane shared-memory ring of the fused tail: one symbol step + two pipeline steps of 64 rows + slack, power of two */
-    b->ring_slots = (int) sdrm_next_pow2((uint64_t) ceilf(sps * 1.01f) + 8 + 2 * 64 + 16 + 8);
-    if (b->ring_slots < 128) {
-        b->ring_slots = 128;
-    }
-    if (b->ring_slots > 1024) {
-        SDRM_LOG_ERROR("samples per symbol %f too large for the fused tail", (double) sps);
-        code = -1;
-        goto fail;
     }
     code = sdrm_dev_zalloc((void **) &b->d_carry, (size_t) b->ring_slots * b->n_ch_pad * sizeof(float));
     if (code != 0) goto fail;
@@ -455,6 +457,40 @@ static int enqueue(sdrm_fsk_demod_batch *b, const void *d_in, size_t in_stride, 
     }
     if (b->aid & SDRM_AID_NO_TAIL) {
         code = 0; /* measurement aid: filters only, no tail (results are meaningless) */
+    } else if (b->unfused) {
+        code = 0;
+        if (b->dc_len > 0) {
+            code = sdrm_launch_code(sdrm_cu_dc_blocker(b->d_ring, 32, (int) b->ring_rows, b->head, n_rows, (int) b->n_ch, b->dc_len,
+                                                       b->d_delay, b->d_sums, ca.pos_l, ca.pos_x, 1, b->s_tail),
+                                    "dc blocker");
+            b->launches += 1;
+        }
+        if (code == 0) {
+            sdrm_clock_args k;
+            memset(&k, 0, sizeof(k));
+            k.ring = b->d_ring;
+            k.tc_stride = 32;
+            k.grouped = 1;
+            k.ring_rows = (int) b->ring_rows;
+            k.head = b->head;
+            k.n_rows = n_rows;
+            k.n_ch = (int) b->n_ch;
+            k.max_history = b->max_history;
+            k.omega_mid = b->omega_mid;
+            k.omega_lim = b->omega_lim;
+            k.gain_omega = b->gain_omega;
+            k.gain_mu = b->gain_mu;
+            k.mmse_taps = b->d_mmse;
+            k.state = b->d_clock;
+            k.soft_out = b->d_soft[slot];
+            k.hard_out = b->d_hard[slot];
+            k.out_stride = b->out_stride;
+            k.out_len = b->d_out_len[slot];
+            k.max_out = ca.max_out;
+            k.error_flag = b->d_error;
+            k.fast = b->fast;
+            code = sdrm_launch_code(sdrm_cu_clock_mm(&k, b->s_tail), "clock recovery");
+        }
     } else {
         code = sdrm_launch_code(sdrm_cu_demod_tail(&ca, b->s_tail), "dc blocker + clock recovery");
     }

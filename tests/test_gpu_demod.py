@@ -306,3 +306,30 @@ def test_random_parameter_sets_bit_exact(sdrm, port, seed):
         assert b.error_flags() == 0
     finally:
         b.close()
+
+
+@pytest.mark.parametrize("use_dc", [True, False])
+def test_samples_per_symbol_beyond_the_fused_tail(sdrm, port, use_dc):
+    """100 baud at 96 ksps without decimation: 960 samples per symbol, a dc blocker of 30720 rows. The fused tail keeps one symbol
+    step of every channel in shared memory and stops at ~855 samples per symbol; beyond that the batch runs the dc blocker and the
+    clock loop as the two plain kernels of tail.cu on the grouped lpf2 ring (the reference accepts any value,
+    src/dsp/fsk_demod.c:53). 34 channels = two channel groups; calls of 50000 samples and a ragged tail."""
+    args = (96000, 100, 5000, 1, 2000, use_dc)
+    shape = workloads.DemodShape("slow", 96000, 100, 5000, 1, 2000, use_dc, 50000)
+    n_ch, n = 34, 230000
+    iq = workloads.gfsk_channels(n_ch, n, shape, seed=77).numpy()
+    b = sdrm.FskDemodBatch(n_ch, *args, 50000, soft=True)
+    checked = (0, 1, 31, 32, 33)
+    oracles = {c: port.FskDemod(*args, 50000) for c in checked}
+    total = 0
+    try:
+        for lo, hi in ((0, 50000), (50000, 100000), (100000, 100003), (100003, 150003), (150003, 150003), (150003, 200003), (200003, n)):
+            hard, lens, soft = b.process(np.ascontiguousarray(iq[:, lo:hi]))
+            for c in checked:
+                oh, os_ = oracles[c].process(iq[c, lo:hi])
+                assert same_bits(hard[c, :lens[c]], oh) and same_bits(soft[c, :lens[c]], os_), (use_dc, lo, c)
+            total += int(lens[0])
+        assert b.error_flags() == 0
+    finally:
+        b.close()
+    assert 200 < total < 260
