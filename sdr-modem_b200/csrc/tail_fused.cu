@@ -448,7 +448,13 @@ __global__ void TAIL_BOUNDS((PROD + 1) * 32) demod_tail_kernel(const sdrm_tail_a
     // uniform register one after the other (R2UR, ~25 cycles apiece). A warp-wide reduction returns its result in a
     // uniform register, which makes the role, the branches on it and the address arithmetic uniform-datapath work
     // (63 -> 12 R2UR in the kernel; the producers' step 2310 -> 2040 cycles).
+#ifdef TAIL_IDLE_WARPS  // A/B builds: TAIL_IDLE_WARPS empty warps between the producers and the clock warp, which moves the
+                        // clock warp to another scheduler of the SM (warp index modulo 4)
+    const int hw_warp = (int) __reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
+    const int warp = hw_warp < PROD ? hw_warp : (hw_warp < PROD + TAIL_IDLE_WARPS ? PROD + 1 : PROD);
+#else
     const int warp = (int) __reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
+#endif
     const int lane = threadIdx.x & 31;
     const int ch0 = blockIdx.x * 32;
     const int ch = ch0 + lane;
@@ -518,6 +524,11 @@ __global__ void TAIL_BOUNDS((PROD + 1) * 32) demod_tail_kernel(const sdrm_tail_a
 
     const uint32_t taps_base = smem_u32(s.taps);
     __syncthreads();
+#ifdef TAIL_IDLE_WARPS
+    if (warp > PROD) {
+        return;
+    }
+#endif
     if (warp < PROD) {
         // ---- producers: PROD pipeline stages in lock step among themselves -------------------------------------------------
         for (int t = 0; t < n_steps - 1; t++) {
@@ -831,7 +842,11 @@ extern "C" int sdrm_cu_demod_tail(const sdrm_tail_args *args, void *stream_ptr) 
             configured[variant][device].store(true, std::memory_order_release);
         }
     }
+#ifdef TAIL_IDLE_WARPS
+    kernel<<<blocks, (prod + 1 + TAIL_IDLE_WARPS) * 32, smem, stream>>>(*args);
+#else
     kernel<<<blocks, (prod + 1) * 32, smem, stream>>>(*args);
+#endif
     err = cudaGetLastError();
     return err == cudaSuccess ? 0 : -(int) err - 1000;
 }
