@@ -358,7 +358,12 @@ def run_other_configs(args, world, rank, local_rank, fp32_peak):
             out.append({"name": "configs[0] one channel on one host core (reference CPU chain, strict build)", "metric": r["metric"],
                         "value": r["value"], "unit": r["unit"], "cpu_cores": 1,
                         "perf_fsk_modem_shape_value": r["shapes"]["perf_fsk_modem_48k_4800"]["msamples_per_s"],
-                        "seconds": r["shapes"]["c1_192k_9600"]["seconds"]})
+                        "seconds": r["shapes"]["c1_192k_9600"]["seconds"],
+                        # the same single stream through this library's one-handle drop-in (one synchronous call per 4096
+                        # samples): the latency-bound path, what the reference's perf_fsk_modem.c times
+                        "gpu_single_handle_value": r["shapes"]["c1_192k_9600"].get("gpu_single_handle_msamples_per_s"),
+                        "gpu_single_handle_perf_shape_value":
+                            r["shapes"]["perf_fsk_modem_48k_4800"].get("gpu_single_handle_msamples_per_s")})
         except Exception as e:
             out.append({"name": "configs[0]", "error": repr(e)[:300]})
     return out

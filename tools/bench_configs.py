@@ -253,10 +253,32 @@ def bench_c1(args):
             iq = workloads.gfsk_channels(1, n, shape, seed=1000, device="cpu").numpy()
         sec, symbols = ref.bench_fsk_demod(*shape.create_args, shape.chunk, iq, 1, passes=1)
         out[name] = {"msamples_per_s": n / sec / 1e6, "seconds": sec, "samples": n, "symbols": int(symbols), "chunk": shape.chunk}
+        try:
+            # the same stream through the library's single-handle drop-in (fsk_demod_create / fsk_demod_process, one synchronous
+            # call per 4096 samples: copy in, five launches, copy out): latency-bound, the path perf_fsk_modem.c measures
+            import torch
+            if torch.cuda.is_available():
+                import time
+                import sdrm
+                warm = sdrm.FskDemod(*shape.create_args, shape.chunk)  # context, module load, first-launch costs
+                warm.process(iq[0, :shape.chunk])
+                warm.close()
+                handle = sdrm.FskDemod(*shape.create_args, shape.chunk)
+                t0 = time.perf_counter()
+                got = 0
+                for o in range(0, n, shape.chunk):
+                    got += len(handle.process(iq[0, o:o + shape.chunk]))
+                gpu_sec = time.perf_counter() - t0
+                handle.close()
+                out[name]["gpu_single_handle_msamples_per_s"] = n / gpu_sec / 1e6
+                out[name]["gpu_single_handle_symbols"] = int(got)
+        except Exception as ex:  # the CPU figure stands on its own
+            out[name]["gpu_single_handle_error"] = str(ex)
     return ({"metric": "demodulated Msamples/s", "value": out["c1_192k_9600"]["msamples_per_s"], "unit": "Msamples/s",
                       "n_gpus": 0, "impl": "reference", "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "1 channel, 1 core, oracle/_ref strict build (BASELINE configs[0])"},
-                      "cpu_baseline": {"cores": 1, "kind": "reference"}, "shapes": out})
+                      "cpu_baseline": {"cores": 1, "kind": "reference"}, "shapes": out,
+                      "gpu_single_handle_value": out["c1_192k_9600"].get("gpu_single_handle_msamples_per_s")})
 
 
 def bench_c3alt(args):
