@@ -179,6 +179,20 @@ static double exp_field(const char *set, int start) {
     return atof(buf);
 }
 
+/* The numeric columns must hold digits, blanks, signs and points only: atof would also read "inf", "nan", hexadecimal and
+ * exponent forms, and an element set from the network (RxRequest.doppler.tle) with such a field — its checksum may still
+ * add up, letters count as zero — would reach the date arithmetic as a non-finite year. The reference's Good_Elements
+ * (src/sgpsdp/sgp_in.c) does not look; such a set is no element set, so it is rejected here. */
+static int numeric_ok(const char *set, int start, int len) {
+    for (int i = start; i < start + len; i++) {
+        const char c = set[i];
+        if (!((c >= '0' && c <= '9') || c == ' ' || c == '.' || c == '+' || c == '-')) {
+            return 0;
+        }
+    }
+    return 1;
+}
+
 int sdrm_orbit_init(const char tle[3][80], sdrm_orbit *orbit) {
     char set[140];
     memset(orbit, 0, sizeof(*orbit));
@@ -190,6 +204,10 @@ int sdrm_orbit_init(const char tle[3][80], sdrm_orbit *orbit) {
     if (strlen(tle[1]) < 69 || strlen(tle[2]) < 69 || !checksum_ok(set) || !checksum_ok(set + 69) || set[0] != '1' || set[69] != '2' ||
         strncmp(set + 2, set + 71, 5) != 0 || set[23] != '.' || set[34] != '.' || set[80] != '.' || set[89] != '.' || set[106] != '.' ||
         set[115] != '.' || set[123] != '.' || strncmp(set + 61, " 0 ", 3) != 0) {
+        return -1;
+    }
+    if (!numeric_ok(set, 18, 14) || !numeric_ok(set, 53, 8) || !numeric_ok(set, 77, 8) || !numeric_ok(set, 86, 8) ||
+        !numeric_ok(set, 95, 7) || !numeric_ok(set, 103, 8) || !numeric_ok(set, 112, 8) || !numeric_ok(set, 121, 10)) {
         return -1;
     }
     char epoch_text[16];

@@ -116,3 +116,13 @@ def test_invalid_element_sets(sdrm):
     assert Orbit(sdrm.lib, bad_checksum).code == -1
     wrong_number = [good[0], good[1], "2 11802" + good[2][7:]]
     assert Orbit(sdrm.lib, wrong_number).code == -1
+    # letters in a numeric column: atof would read "inf" / "nan" / an exponent form, and the checksum (letters count as zero)
+    # can be made to agree; such a set is rejected before it reaches the date arithmetic (found by fuzzing under UBSan)
+    def with_checksum(line):
+        total = sum(int(c) if c.isdigit() else (1 if c == "-" else 0) for c in line[:68])
+        return line[:68] + str(total % 10)
+    for column, text in ((18, "inf"), (20, "nan"), (26, "e9"), (53, "0x1")):
+        line1 = good[1][:column] + text + good[1][column + len(text):]
+        assert Orbit(sdrm.lib, [good[0], with_checksum(line1), good[2]]).code == -1, text
+    short = [good[0], good[1][:40], good[2]]
+    assert Orbit(sdrm.lib, short).code == -1
