@@ -249,3 +249,56 @@ def test_rx_group_stops_serving_a_client_whose_socket_fails(sdrm, port):
     got = np.frombuffer(b"".join(chunks), dtype=np.int8)
     want, _ = port.FskDemod(*args, 4096).run(iq, 4096)
     assert same_bits(got, want)
+
+
+def test_create_destroy_cycles_release_device_and_pinned_memory(sdrm):
+    """Every handle type created, used once and destroyed 25 times over: the device's free memory comes back to where it
+    was (cudaMemGetInfo; a leaked staging buffer of these sizes would show as tens of MB per cycle), and so does the
+    process's pinned host memory as far as the resident set shows it."""
+    import resource
+
+    import torch
+    from conftest import LUCKY7_TLE
+    from test_gpu_doppler import LAT, LON, DopplerHandle
+
+    rng = np.random.default_rng(3)
+    iq = (rng.standard_normal((8, 20000)) + 1j * rng.standard_normal((8, 20000))).astype(np.complex64)
+    data = rng.integers(0, 256, (8, 256), dtype=np.uint8)
+
+    def cycle():
+        b = sdrm.FskDemodBatch(8, 192000, 9600, 5000, 2, 2000, True, 20000, soft=True)
+        b.process(iq)
+        b.submit_i16(np.zeros((8, 20000, 2), np.int16))
+        b.fetch()
+        b.close()
+        h = sdrm.FskDemod(48000, 4800, 5000, 2, 2000, True, 20000)
+        h.process(iq[0])
+        h.close()
+        m = sdrm.GfskModBatch(8, 2.0, 1.6, 0.5, 256)
+        m.process(data)
+        m.close()
+        lp = sdrm.LpfBatch(8, 4, 192000, 10000, 2000, 20000, True)
+        lp.process(iq)
+        lp.close()
+        nco = sdrm.NcoBatch(8, 1.0, 192000, 20000)
+        nco.multiply(np.arange(8) * 100, iq)
+        nco.close()
+        d = DopplerHandle(sdrm.lib, LAT, LON, 0.0, 48000, 437525000, 0, 1583840449, 20000, LUCKY7_TLE)
+        d.run(iq[0], 20000)
+        d.close()
+        multi = sdrm.FskDemodMulti([0], 8, 192000, 9600, 5000, 2, 2000, True, 20000)
+        multi.process(iq)
+        multi.close()
+
+    for _ in range(3):
+        cycle()  # first-use allocations of the runtime itself (module load, stream pools, the allocator's own pools)
+    torch.cuda.synchronize()
+    free_before, _ = torch.cuda.mem_get_info()
+    rss_before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    for _ in range(25):
+        cycle()
+    torch.cuda.synchronize()
+    free_after, _ = torch.cuda.mem_get_info()
+    rss_after = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    assert free_before - free_after < 8 << 20, "device memory went down by %.1f MB over 25 cycles" % ((free_before - free_after) / 2 ** 20)
+    assert rss_after - rss_before < 64 * 1024, "peak resident set grew by %d KB over 25 cycles" % (rss_after - rss_before)
