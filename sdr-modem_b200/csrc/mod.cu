@@ -26,7 +26,6 @@ namespace {
 constexpr float kTwoPi = 6.283185307179586476925286766559f;  // (float) (2 * M_PI), frequency_modulator.c:11
 constexpr int kMaxBranchTaps = 64;
 constexpr int kTileRows = 32;              // time steps per shared-memory tile of the walker
-constexpr int kTile = kTileRows * 32;      // floats per [time][lane] tile (4 KB)
 
 // Intermediate layout between the three passes ("GTC", as in the demod tail): float [group][time][32 channels], so that
 // the serial pass, whose lanes are channels, moves 32 time steps of its 32 channels as one contiguous 4 KB tile.
@@ -104,14 +103,36 @@ __global__ void interp_shape_kernel(const sdrm_interp_args a) {
 // packets (lane = channel), so the bytes are read once, the +-1 samples never exist as floats (multiplying a tap by
 // +-1 is a sign flip, exact) and every store is a full 128-byte row of the GTC layout.
 // The first word also needs the carried history (floats, zero before the first call) and takes the general route.
+// A shaped sample depends on K consecutive bits only: with the window's bits as an index, all 2^K x I values are computed once
+// per CTA into shared memory — by the same sequence of additions, tap 0 first, and the same scaling the direct form uses, so
+// the table holds bit for bit what the direct form would produce — and an output costs a shift, a mask, a load and a store
+// instead of K sign flips and K additions per branch. LUT = false is the direct form (tables of more than 32 KB: K = 8 with
+// more than 32 branches does not occur; kept for the A/B comparison and as the definition of the table's contents).
+template <bool LUT>
 __global__ void __launch_bounds__(256) bits_shape_kernel(const sdrm_interp_args a) {
     __shared__ float taps_s[8 * 32];  // [p][j]; the launcher checks K <= 8 and I <= 32
+    extern __shared__ float lut_s[];  // LUT: [window bits][p]
     const int K = a.branch_taps;
     const int I = a.interpolation;
     for (int i = threadIdx.x; i < K * I; i += blockDim.x) {
         taps_s[i] = a.taps_rev[i];
     }
     __syncthreads();
+    if (LUT) {
+        // bit (K - 1 - j) of the index is window sample j; a clear bit is the sample -1, i.e. the tap with its sign flipped
+        for (int e = threadIdx.x; e < (I << K); e += blockDim.x) {
+            const int w = e / I;
+            const int p = e - w * I;
+            const float *rev = taps_s + p * K;
+            float acc = 0.0f;
+            for (int j = 0; j < K; j++) {
+                const uint32_t flip = ((w >> (K - 1 - j)) & 1) ? 0u : 0x80000000u;
+                acc = __fadd_rn(acc, __uint_as_float(__float_as_uint(rev[j]) ^ flip));
+            }
+            lut_s[e] = a.apply_scale ? __fmul_rn(a.scale, acc) : acc;
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int ch = blockIdx.y * 32 + lane;
     const int chc = ch < a.n_ch ? ch : a.n_ch - 1;
@@ -156,24 +177,44 @@ __global__ void __launch_bounds__(256) bits_shape_kernel(const sdrm_interp_args 
             continue;
         }
         const uint64_t comb = ((uint64_t) load_word(wi - 1) << 32) | cur;
-        for (int kk = 0; kk < nk; kk++) {
-            // bit (K - 1 - j) of x is window sample j; a clear bit is the sample -1, i.e. a flipped tap sign
-            const uint32_t flips = ~(uint32_t) (comb >> (31 - kk));
-            uint32_t sgn[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                sgn[j] = (flips << (31 - (K - 1 - j))) & 0x80000000u;  // shift counts of absent taps are unused
-            }
-            for (int p = 0; p < I; p++) {
-                const float *rev = taps_s + p * K;
-                float acc = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (j < K) {
-                        acc = __fadd_rn(acc, __uint_as_float(__float_as_uint(rev[j]) ^ sgn[j]));
+        if (LUT) {
+            const uint32_t mask = (1u << K) - 1u;
+            if (I == 2) {
+                const float2 *lut2 = reinterpret_cast<const float2 *>(lut_s);
+                for (int kk = 0; kk < nk; kk++) {
+                    const float2 v = lut2[(uint32_t) (comb >> (31 - kk)) & mask];
+                    float *dst = out + ((size_t) (k0 + kk) << 6);
+                    dst[0] = v.x;
+                    dst[32] = v.y;
+                }
+            } else {
+                for (int kk = 0; kk < nk; kk++) {
+                    const float *row = lut_s + ((uint32_t) (comb >> (31 - kk)) & mask) * I;
+                    for (int p = 0; p < I; p++) {
+                        out[((size_t) (k0 + kk) * I + p) << 5] = row[p];
                     }
                 }
-                out[((size_t) (k0 + kk) * I + p) << 5] = a.apply_scale ? __fmul_rn(a.scale, acc) : acc;
+            }
+        } else {
+            for (int kk = 0; kk < nk; kk++) {
+                // bit (K - 1 - j) of x is window sample j; a clear bit is the sample -1, i.e. a flipped tap sign
+                const uint32_t flips = ~(uint32_t) (comb >> (31 - kk));
+                uint32_t sgn[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    sgn[j] = (flips << (31 - (K - 1 - j))) & 0x80000000u;  // shift counts of absent taps are unused
+                }
+                for (int p = 0; p < I; p++) {
+                    const float *rev = taps_s + p * K;
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (j < K) {
+                            acc = __fadd_rn(acc, __uint_as_float(__float_as_uint(rev[j]) ^ sgn[j]));
+                        }
+                    }
+                    out[((size_t) (k0 + kk) * I + p) << 5] = a.apply_scale ? __fmul_rn(a.scale, acc) : acc;
+                }
             }
         }
     }
@@ -409,7 +450,16 @@ extern "C" int sdrm_cu_interp_fir(const sdrm_interp_args *a, void *stream_ptr) {
                     long long wx = (((long long) a->n_in + 31) / 32 + 7) / 8;
                     const long long want = (148LL * 8 + grid.y - 1) / grid.y;
                     dim3 wgrid((unsigned) (wx < want ? wx : want), grid.y);
-                    bits_shape_kernel<<<wgrid, 256, 0, stream>>>(*a);
+                    const size_t lut_bytes = ((size_t) a->interpolation << a->branch_taps) * sizeof(float);
+#ifdef MOD_NO_LUT  // A/B builds
+                    bits_shape_kernel<false><<<wgrid, 256, 0, stream>>>(*a);
+#else
+                    if (lut_bytes <= 32768) {
+                        bits_shape_kernel<true><<<wgrid, 256, lut_bytes, stream>>>(*a);
+                    } else {
+                        bits_shape_kernel<false><<<wgrid, 256, 0, stream>>>(*a);
+                    }
+#endif
                 } else if (a->branch_taps <= 8) {
                     interp_shape_kernel<true, true, 8><<<grid, 256, 0, stream>>>(*a);
                 } else {
