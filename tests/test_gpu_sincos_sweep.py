@@ -5,7 +5,7 @@ sig_source.c). The kernels compute the same through one device function (csrc/de
 routines that are each accurate to an ulp or so agree after rounding to float except when the true value sits within a few
 double ulps of a float rounding boundary — about one value in 10^8 — so "it matched on the test signals" is not a proof. The
 phase is a float that the wrap keeps inside [-2 pi, 2 pi] (frequency_modulator.c:50-55, sig_source.c), which is few enough
-values to try them all: 2 x 1 086 918 620 floats. This test sweeps all of them against libm on the host (the oracle's C side);
+values to try them all: 2 x 1 088 425 985 floats (up to 7.0). This test sweeps all of them against libm on the host (the oracle's C side);
 SDRM_SINCOS_SWEEP=quick limits it to every 61st block for a fast run."""
 import ctypes as C
 import os
@@ -17,6 +17,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 TWO_PI_BITS = struct.unpack("<I", struct.pack("<f", 6.283185307179586))[0]  # 0x40C90FDB
+# the wrap compares with > and <, so +-2 pi itself is a phase; the sweep runs on to 7.0 for margin
+LAST_BITS = struct.unpack("<I", struct.pack("<f", 7.0))[0] + 4096
 BLOCK = 1 << 24
 
 
@@ -24,7 +26,7 @@ def sweep(sdrm, sincos_sweep, sign_bit, stride_blocks):
     lib = sdrm.lib
     lib.sdrm_cu_selftest_sincos.argtypes = [C.c_uint32, C.c_size_t, C.c_void_p]
     lib.sdrm_cu_selftest_sincos.restype = C.c_int
-    last = TWO_PI_BITS + 64  # a little past 2 pi: the wrap compares with > and <, so 2 pi itself is a phase
+    last = LAST_BITS
     out = np.empty((BLOCK, 2), np.float32)
     checked = 0
     bad_total = 0
