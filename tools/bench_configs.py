@@ -99,7 +99,7 @@ def bench_c4(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                      "note": "8.06 algorithmic B per output sample; bounded by the serial float phase recurrence (one lane per "
                              "channel, 20.5 cycles per sample: 0.34 ms per 32768-sample packet whatever the channel count, up to "
-                             "148 SMs x 4 warps x 32 lanes = 18944 channels) and, past that, by the double-precision sincos"},
+                             "148 SMs x 4 warps x 32 lanes = 18944 channels) and, past that, by the 24 B per sample the three passes (shaping, walk, cos / sin) move through HBM"},
         "cpu_baseline": cpu, "gpu_launches": launches})
 
 
