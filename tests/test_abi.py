@@ -161,3 +161,16 @@ def test_division_steps_check_runs_on_the_host(sdrm):
     for length in (320, 160, 107, 32, 3, 33333):
         assert steps(length) == 1
     assert steps(0) == 0
+
+
+def test_every_public_header_compiles_on_its_own_as_c99(tmp_path):
+    """a host that includes one header must not need another one first (the reference's headers have the same property), and
+    nothing in them goes beyond C99"""
+    headers = sorted(glob.glob(os.path.join(ROOT, "include", "sdrm", "*.h")))
+    assert len(headers) >= 20
+    for header in headers:
+        source = tmp_path / "one.c"
+        source.write_text('#include "%s"\nint main(void) { return 0; }\n' % header)
+        proc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-c", str(source), "-o", str(tmp_path / "one.o")],
+                              capture_output=True, text=True)
+        assert proc.returncode == 0, "%s:\n%s" % (os.path.basename(header), proc.stderr[:2000])
